@@ -1,0 +1,222 @@
+"""Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+It imports /root/reference/utils/similarity.py by path (it depends on torch only) and drives
+  * mae_simsearch      (utils/similarity.py:37-132) through a latent-cache stub model and a
+                       sliceable loader, so the reference code runs unchanged over a
+                       pre-encoded bank; bank indices are recovered from ra_dec[:, 0];
+  * compute_similarity (:214-268) directly;
+  * update_best_scores (:18-35) directly, including NaN / inf / tie inputs.
+Inputs come from sky_embeddings_b200.synth (seeded numpy PCG64); the fixtures store the seeds,
+an input checksum and the reference's outputs.  The reference cannot travel to the GPU box, the
+fixtures do.  Nothing here is imported by the product.
+"""
+from __future__ import annotations
+
+import contextlib
+import hashlib
+import importlib.util
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sky_embeddings_b200 import synth  # noqa: E402
+
+REF = "/root/reference/utils/similarity.py"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def load_reference():
+    spec = importlib.util.spec_from_file_location("ref_similarity", REF)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class LatentStub:
+    """Stands in for the ViT: the 'images' it is fed are already latents."""
+
+    def __init__(self, num_extra_tokens=1):
+        self.num_extra_tokens = num_extra_tokens
+
+    def eval(self):
+        return self
+
+    def forward_features(self, samples, ra_dec=None, reshape_out=False):
+        return samples, None, None
+
+
+class LatentLoader:
+    """Flat loader over a latent bank: yields (latents[B,...], mask, ra_dec[B,2]);
+    ra_dec[:,0] = bank row (exact in f32 below 2**24), ra_dec[:,1] = 0."""
+
+    def __init__(self, bank, batch_size):
+        self.bank = torch.as_tensor(bank)
+        self.bs = batch_size
+
+    def __len__(self):
+        return (self.bank.shape[0] + self.bs - 1) // self.bs
+
+    def __iter__(self):
+        n = self.bank.shape[0]
+        for s in range(0, n, self.bs):
+            e = min(n, s + self.bs)
+            ra = torch.zeros((e - s, 2), dtype=torch.float32)
+            ra[:, 0] = torch.arange(s, e, dtype=torch.float32)
+            yield self.bank[s:e], torch.zeros(e - s), ra
+
+
+def checksum(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]
+
+
+def quiet(fn, *a, **kw):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **kw)
+
+
+def simsearch_cases(ref):
+    """mae_simsearch over small latent banks: every metric x token mode x combine x weights."""
+    out = {}
+    n, P, D, bs, k = 600, 4, 48, 64, 20
+    seed = synth.BASE_SEED
+    bank = synth.latents(n, 1 + P, D, seed=seed, stream=11)
+    tgt = synth.target_group(bank, [17, 333], copies=7, noise=0.3, seed=seed, stream=12)
+    out["meta"] = np.array([n, P, D, bs, k, seed, 11, 12, 7], dtype=np.int64)
+    out["anchors"] = np.array([17, 333], dtype=np.int64)
+    out["noise"] = np.float32(0.3)
+    out["checksum"] = np.array(checksum(bank, tgt))
+    names = []
+    modes = [("maxpool", dict(max_pool=True, cls_token=False), ["min"]),
+             ("cls", dict(max_pool=False, cls_token=True), ["min"]),
+             ("patches", dict(max_pool=False, cls_token=False), ["mean", "min", "max"])]
+    for metric in ("cosine", "MSE", "MAE"):
+        for mname, mkw, combines in modes:
+            for combine in combines:
+                for uw in (True, False):
+                    name = f"{metric}.{mname}.{combine}.{'w' if uw else 'u'}"
+                    res = quiet(ref.mae_simsearch, LatentStub(1), torch.from_numpy(tgt),
+                                LatentLoader(bank, bs), "cpu", metric=metric, combine=combine,
+                                use_weights=uw, nested_batches=False, n_save=k, **mkw)
+                    best_samples, best_latent, best_ra, best_scores = res
+                    idx = best_ra[:, 0].numpy().astype(np.int64)
+                    assert np.array_equal(best_samples.numpy(), bank[idx]), name
+                    out[f"scores.{name}"] = best_scores.numpy()
+                    out[f"idx.{name}"] = idx
+                    names.append(name)
+    out["names"] = np.array(names)
+    return out
+
+
+def mim1_shape_case(ref):
+    """BASELINE config 1 shape: D=768 (configs/mim_1.ini:26), max-pooled (L=1), cosine,
+    use_weights=True, k=10, batch 64 -- on synthetic latents (no ViT weights offline)."""
+    out = {}
+    n, P, D, bs, k = 2000, 8, 768, 64, 10
+    seed = synth.BASE_SEED
+    bank = synth.latents(n, 1 + P, D, seed=seed, stream=21)
+    tgt = synth.target_group(bank, [5, 1234], copies=65, noise=0.5, seed=seed, stream=22)
+    out["meta"] = np.array([n, P, D, bs, k, seed, 21, 22, 65], dtype=np.int64)
+    out["anchors"] = np.array([5, 1234], dtype=np.int64)
+    out["noise"] = np.float32(0.5)
+    out["checksum"] = np.array(checksum(bank, tgt))
+    for metric in ("cosine", "MSE"):
+        res = quiet(ref.mae_simsearch, LatentStub(1), torch.from_numpy(tgt), LatentLoader(bank, bs),
+                    "cpu", metric=metric, combine="min", use_weights=True, max_pool=True,
+                    cls_token=False, nested_batches=False, n_save=k)
+        out[f"scores.{metric}"] = res[3].numpy()
+        out[f"idx.{metric}"] = res[2][:, 0].numpy().astype(np.int64)
+    return out
+
+
+def short_bank_case(ref):
+    """N < n_save: the +-inf initial fill leaks into the result (utils/similarity.py:65-66)."""
+    out = {}
+    n, P, D, bs, k = 12, 2, 16, 8, 20
+    seed = synth.BASE_SEED
+    bank = synth.latents(n, 1 + P, D, seed=seed, stream=31)
+    tgt = synth.target_group(bank, [3], copies=5, noise=0.3, seed=seed, stream=32)
+    out["meta"] = np.array([n, P, D, bs, k, seed, 31, 32, 5], dtype=np.int64)
+    out["checksum"] = np.array(checksum(bank, tgt))
+    for metric in ("cosine", "MSE"):
+        res = quiet(ref.mae_simsearch, LatentStub(1), torch.from_numpy(tgt), LatentLoader(bank, bs),
+                    "cpu", metric=metric, combine="mean", use_weights=True, max_pool=False,
+                    cls_token=False, nested_batches=False, n_save=k)
+        out[f"scores.{metric}"] = res[3].numpy()
+        # rows >= n are torch.empty garbage in the reference: keep only the valid prefix
+        out[f"idx.{metric}"] = res[2][:n, 0].numpy().astype(np.int64)
+    return out
+
+
+def compute_similarity_cases(ref):
+    out = {}
+    seed = synth.BASE_SEED
+    T, L, D, B = 9, 6, 32, 50
+    target = synth.latents(T, L, D, seed=seed, stream=41)
+    test = synth.latents(B, L, D, seed=seed, stream=42)
+    out["meta"] = np.array([T, L, D, B, seed, 41, 42], dtype=np.int64)
+    out["checksum"] = np.array(checksum(target, test))
+    names = []
+    for metric in ("cosine", "MSE", "MAE"):
+        for combine in ("mean", "min", "max"):
+            for uw in (True, False):
+                for nts in (None, 2):
+                    name = f"{metric}.{combine}.{'w' if uw else 'u'}.{nts}"
+                    s = ref.compute_similarity(torch.from_numpy(target), torch.from_numpy(test),
+                                               metric=metric, combine=combine, use_weights=uw,
+                                               n_top_sims=nts)
+                    out[f"scores.{name}"] = s.numpy()
+                    names.append(name)
+    out["names"] = np.array(names)
+    t, w = ref.determine_target_features(torch.from_numpy(target))
+    out["t"] = t.numpy()
+    out["w"] = w.numpy()
+    return out
+
+
+def update_best_cases(ref):
+    """update_best_scores with NaN / inf / ties: fixes the NaN-is-largest ordering."""
+    out = {}
+    best = torch.tensor([0.9, 0.5, float("-inf"), float("-inf")])
+    new = torch.tensor([0.5, float("nan"), 0.7, float("inf"), -1.0, 0.5])
+    pay_b = torch.arange(4, dtype=torch.float32).view(4, 1)
+    pay_n = torch.arange(4, 10, dtype=torch.float32).view(6, 1)
+    ra_b = torch.stack([torch.arange(4.), torch.zeros(4)], 1)
+    ra_n = torch.stack([torch.arange(4., 10.), torch.zeros(6)], 1)
+    out["best"] = best.numpy()
+    out["new"] = new.numpy()
+    for metric in ("cosine", "MSE"):
+        b = best if metric == "cosine" else -best
+        s, ra, sc = ref.update_best_scores(pay_n, ra_n, new, pay_b, ra_b, b, 4, metric)
+        out[f"scores.{metric}"] = sc.numpy()
+        out[f"src.{metric}"] = ra[:, 0].numpy().astype(np.int64)
+    return out
+
+
+def main():
+    ref = load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(1)   # deterministic reduction order for the fixtures
+    for name, fn in (("simsearch_small", simsearch_cases), ("simsearch_mim1_shape", mim1_shape_case),
+                     ("short_bank", short_bank_case), ("compute_similarity", compute_similarity_cases),
+                     ("update_best", update_best_cases)):
+        data = fn(ref)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"wrote {path} ({os.path.getsize(path)} B, {len(data)} arrays)")
+
+
+if __name__ == "__main__":
+    main()
