@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the similarity-search hot path (BASELINE.json metric: queries/sec of exact top-k
+over an N-vector bank, plus % of the HBM / tensor roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3s]
+
+N = 1 workload (BASELINE.json configs[1], "C2"): 1M-vector x 768 bf16 bank resident in HBM,
+64 queries, cosine, top-100.  One step = one pass of the hot path over one query batch
+(pack queries -> tcgen05 scoring kernel with fused top-k -> merge of per-CTA candidates).
+N > 1 (torchrun, one rank per GPU): every rank holds its own 1M-vector shard (weak scaling; the
+bank is N x 1M vectors), each step adds one NCCL all-gather of the per-rank [Q, k] candidates and a
+device merge.  `value` counts query-over-1M-vector-shard searches per second over all ranks
+(= N*Q/t); `qps_global_bank` is Q/t over the whole N x 1M bank.
+
+--impl reference times the reference's own CPU algorithm (oracle/ref_port.py, a torch port of
+/root/reference/utils/similarity.py: the reference is pure Python and cannot travel to the GPU
+box) on the host cores, each step a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec exact top-k over N-vector bank"
+WORKLOADS = {
+    # name: (bank rows per GPU, D, Q, k, metric)
+    "c2": (1_000_000, 768, 64, 100, "cosine"),
+    "c2mse": (1_000_000, 768, 64, 100, "MSE"),
+    "small": (100_000, 768, 64, 100, "cosine"),
+}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def read_traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the scoring kernel, from the committed
+    ncu --set full capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        return d.get("simt" if path == "simt" else "tensor")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the GPU works."""
+
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.window = None          # (t0, t1) of the timed region, set by the caller
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:   # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, util, r))
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        inside = [s for s in self.samples if self.window and self.window[0] <= s[0] <= self.window[1]]
+        note = "sampled inside the timed region"
+        if len(inside) < 3:
+            inside = self.samples
+            note = "timed region shorter than the sampling period: warm-up + timed + same-work burst window"
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(inside), "note": note}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (the reference's algorithm on host cores)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(D, k, metric, rows, n_queries, batch=512, seed=0):
+    """Time oracle/ref_port.multi_query_loop on `rows` bank rows x n_queries queries."""
+    import torch
+    from oracle import ref_port
+    from sky_embeddings_b200 import synth
+    s, m = synth.feature_profile(D)
+    g = torch.Generator().manual_seed(seed)
+    bank = torch.randn((rows, D), generator=g) * torch.from_numpy(s) + torch.from_numpy(m)
+    mu, sd = bank[:batch].mean(0), bank[:batch].std(0)
+    z = ((bank - mu) / (sd + 1e-8)).unsqueeze(1)
+    q = z[:: max(rows // n_queries, 1), 0][:n_queries] + 0.1 * torch.randn((n_queries, D), generator=g)
+    t0 = time.perf_counter()
+    ref_port.multi_query_loop(q, None, z, batch, k, metric)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_block(n_bank, D, Q, k, metric, budget_s=15.0):
+    import torch
+    cores = torch.get_num_threads()
+    rows = min(n_bank, 100_000)
+    cpu_sample(D, k, metric, min(rows, 20_000), 1)            # warm-up
+    t1 = cpu_sample(D, k, metric, rows, 1)
+    nq = int(max(1, min(16, budget_s / max(t1, 1e-3))))
+    t = cpu_sample(D, k, metric, rows, nq) if nq > 1 else t1
+    per_query_full = t / nq * (n_bank / rows)
+    return {"value": 1.0 / per_query_full, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/ref_port.py (torch {torch.__version__} CPU port of utils/similarity.py, one pass per "
+                      f"query as the reference requires): {nq} of {Q} queries over the first {rows} of {n_bank} "
+                      f"bank rows, batch 512, {t:.2f} s, scaled linearly to the full bank"}
+
+
+def run_reference(args, wl):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return 0
+    import torch
+    n_bank, D, Q, k, metric = wl
+    cores = torch.get_num_threads()
+    # bounded sample: size one step so that the whole --steps/--warmup run ends within ~2 minutes
+    nq = 1
+    probe_rows = min(n_bank, 20_000)
+    cpu_sample(D, k, metric, probe_rows, nq)
+    rows_per_s = probe_rows / max(cpu_sample(D, k, metric, probe_rows, nq), 1e-6)
+    budget = 120.0 / max(args.steps + args.warmup, 1)
+    rows = int(min(n_bank, 100_000, max(4096, rows_per_s * budget)))
+    for _ in range(args.warmup):
+        cpu_sample(D, k, metric, rows, nq)
+    times = []
+    for _ in range(args.steps):
+        times.append(cpu_sample(D, k, metric, rows, nq))
+    per_step = sum(times) / len(times)
+    # one step = nq queries over `rows` rows.  Same unit as the GPU arm's `value`: searches of one query over
+    # one n_bank-vector shard per second (the CPU has no shards to spread over, so this does not grow with N)
+    qps = nq / (per_step * (n_bank / rows))
+    sample = (f"each step: {nq} query over the first {rows} of {n_bank * world} bank rows with oracle/ref_port.py "
+              f"(torch {torch.__version__} CPU port of utils/similarity.py), scaled linearly")
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "bank_vectors": n_bank * world, "dim": D, "queries": Q, "k": k,
+                       "similarity": metric},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def build_bank(n_rows, D, dev, row0_chunk=0):
+    """Device-generated synthetic shard: chunks [row0_chunk, ...) of the global synthetic bank,
+    normalised with the statistics of the first 512 rows of global chunk 0 on every rank."""
+    from sky_embeddings_b200 import Bank, synth
+    bank = Bank(n_rows, 1, D, "bf16", dev)
+    first = synth.device_bank_chunk(0, 512, D, dev)
+    bank.fit_norm(first)
+    done = 0
+    c = row0_chunk
+    while done < n_rows:
+        rows = min(synth.CHUNK_ROWS, n_rows - done)
+        bank.upload(synth.device_bank_chunk(c, rows, D, dev), done)
+        done += rows
+        c += 1
+    return bank.finalize()
+
+
+def run_gpu(args, wl):
+    import torch
+    import torch.distributed as dist
+    from sky_embeddings_b200 import _lib, synth
+    from sky_embeddings_b200.distributed import gather_candidates
+    from sky_embeddings_b200.engine import merge_candidates
+
+    rank, local, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the search path has no CPU fallback")
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_bank, D, Q, k, metric = wl
+    chunks_per_rank = (n_bank + synth.CHUNK_ROWS - 1) // synth.CHUNK_ROWS
+    row_lo = rank * n_bank
+    bank = build_bank(n_bank, D, dev, row0_chunk=rank * chunks_per_rank)
+
+    # queries: planted neighbours of rows of THIS process's rank-0 shard layout (same on every rank:
+    # generated from global chunk 0 with the shared statistics)
+    probe = build_bank(min(n_bank, synth.CHUNK_ROWS), D, dev, row0_chunk=0)
+    stride = probe.n_items // Q
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    planted = [q * stride + stride // 2 for q in range(Q)]
+    t_dev = torch.cat([probe.download(r, 1)[:, 0] for r in planted])
+    t_dev = t_dev + 0.1 * torch.randn((Q, D), generator=gen, device=dev)
+    probe.close()
+    t_host = t_dev.cpu().pin_memory()
+    out_s_host = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+    out_i_host = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+
+    def step_device():
+        s, i = bank.search(t_dev, None, k=k, metric=metric, path=args.path, idx_offset=row_lo)
+        if world > 1:
+            gs, gi = gather_candidates(s, i)
+            s, i = merge_candidates(gs, gi, k, metric)
+        return s, i
+
+    def step_host():
+        # public API with HOST buffers: H2D of the queries and D2H of the results inside the call
+        if world == 1:
+            return bank.search_host(t_host, None, k=k, metric=metric, path=args.path, idx_offset=row_lo,
+                                    out_scores=out_s_host, out_idx=out_i_host)
+        td = t_host.to(dev, non_blocking=True)
+        s, i = bank.search(td, None, k=k, metric=metric, path=args.path, idx_offset=row_lo)
+        gs, gi = gather_candidates(s, i)
+        s, i = merge_candidates(gs, gi, k, metric)
+        out_s_host.copy_(s, non_blocking=True)
+        out_i_host.copy_(i, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_s_host, out_i_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # correctness gate before timing: the planted rows must come back first on rank 0's shard
+    s, i = step_device()
+    torch.cuda.synchronize()
+    if True:
+        assert i[:, 0].cpu().tolist() == planted, "planted nearest neighbours not returned: refusing to time a wrong kernel"
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    bank.profile(True)
+    bank.profile_read(reset=True)
+    _lib.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    sampler.window = (t_wall0, t_wall1)
+    launches = _lib.launch_count(reset=True)
+    ms_total = ev0.elapsed_time(ev1)
+    n_kern, kern_ms = bank.profile_read(reset=True)
+    bank.profile(False)
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+
+    # end-to-end through the host-buffer API
+    for _ in range(3):
+        step_host()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_host()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e_step = e2e_ms / args.steps
+
+    # keep the GPU busy with the same work long enough for the clock sampler if the run was short
+    if (t_wall1 - t_wall0) < 0.05:
+        t_end = time.perf_counter() + 0.3
+        while time.perf_counter() < t_end:
+            step_device()
+        torch.cuda.synchronize()
+    sampler.stop()
+    sampler.join(timeout=1.0)
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        kern_avg_ms = kern_ms / max(n_kern, 1)
+        algo_bytes = float(n_bank) * D * 2                      # one pass over this GPU's bf16 shard
+        achieved = algo_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else 0.0
+        value = world * Q / (ms_step * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n_bank}-vector x {D} bf16 bank per GPU ({n_bank * world} total), "
+                                   f"{Q} queries, {metric} top-{k}, exact",
+                       "bank_vectors_per_gpu": n_bank, "bank_vectors": n_bank * world, "dim": D, "queries": Q, "k": k,
+                       "similarity": metric, "path": args.path, "parallelism": f"row-shard x{world}",
+                       "l2_policy": f"bank shard ({algo_bytes / 1e6:.0f} MB) is larger than the 126 MB L2; no flush needed",
+                       "value_definition": "N_gpus * Q / step time (query-over-1M-vector-shard searches/s; at N=1 plain QPS)"},
+            "qps_global_bank": Q / (ms_step * 1e-3),
+            "clocks": sampler.summary(),
+            "e2e": {"value": world * Q / (e2e_step * 1e-3), "unit": "queries/s", "ms_per_step": e2e_step,
+                    "h2d_bytes_per_step": t_host.numel() * 4, "d2h_bytes_per_step": Q * k * 12,
+                    "api": "sky_search_host (C ABI, pinned host buffers)" if world == 1 else
+                           "pinned H2D + sky_search + NCCL all-gather + sky_merge_candidates + D2H"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": read_traffic(args.path),
+                         "kernel": "tc_search_kernel<64>" if args.path != "simt" else "simt_search_kernel",
+                         "kernel_ms": kern_avg_ms, "kernel_launches": n_kern, "algorithmic_bytes": algo_bytes,
+                         "peak_source": peak_src, "kernel_share_of_step": kern_avg_ms * (n_kern / args.steps) / ms_step},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_block(n_bank, D, Q, k, metric)
+        print(json.dumps(line), flush=True)
+    bank.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    return run_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

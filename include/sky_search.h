@@ -1,0 +1,148 @@
+/* sky_search.h -- C ABI of the B200-native similarity-search engine (libskysearch.so).
+ *
+ * Drop-in boundary for ONE path of teaghan/sky_embeddings: utils/similarity.py as driven by
+ * similarity_search.py / sky_sim_search.py.  The reference has no FFI layer (it is pure Python,
+ * SURVEY.md section 8(b)); each entry point below cites the reference code it replaces, and
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns int: 0 = ok, negative = error (text via sky_last_error());
+ *  - no exceptions, no torch / C++ types across the ABI;
+ *  - every pointer is a DEVICE pointer unless its name starts with h_;
+ *  - every call takes a cudaStream_t (passed as void*) and is asynchronous on it, except the
+ *    *_host variants, which copy host<->device and synchronise the stream before returning;
+ *  - a bank handle is bound to one device; calls on one handle must be externally serialised.
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with SKY_ERR_CUDA.
+ */
+#ifndef SKY_SEARCH_H_
+#define SKY_SEARCH_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKY_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SKY_API __attribute__((visibility("default")))
+#else
+#define SKY_API
+#endif
+
+/* status codes */
+#define SKY_OK            0
+#define SKY_ERR_ARG      -1   /* invalid argument (incl. unknown metric: the reference raises
+                                 UnboundLocalError there, utils/similarity.py:250-259) */
+#define SKY_ERR_CUDA     -2   /* CUDA runtime / driver error */
+#define SKY_ERR_STATE    -3   /* call order violated (e.g. search before finalize) */
+#define SKY_ERR_NOMEM    -4
+#define SKY_ERR_UNSUPPORTED -5
+
+/* element types of bank storage / upload sources */
+#define SKY_F32   0
+#define SKY_BF16  1
+
+/* metrics: utils/similarity.py:149-212; selection order :20-29 (cosine descending, others ascending) */
+#define SKY_COSINE 0
+#define SKY_MSE    1
+#define SKY_MAE    2
+
+/* combine over the L tokens of an item: utils/similarity.py:262-267 */
+#define SKY_MEAN 0
+#define SKY_MIN  1
+#define SKY_MAX  2
+
+/* token selection applied to encoder output [B, tokens, D]: utils/similarity.py:55-63, :87-95 */
+#define SKY_TOK_ALL      0   /* rows are used as given (tokens == L) */
+#define SKY_TOK_CLS      1   /* keep token 0                      (cls_token=True)  -> L = 1 */
+#define SKY_TOK_PATCHES  2   /* drop the first num_extra_tokens   (max_pool=False)  -> L = tokens - extra */
+#define SKY_TOK_MAXPOOL  3   /* drop extras, max over patches     (max_pool=True)   -> L = 1 */
+
+/* kernel path */
+#define SKY_PATH_AUTO    0
+#define SKY_PATH_SIMT    1   /* HBM-streaming warp-reduction kernel (any dtype / metric / weights / L) */
+#define SKY_PATH_TENSOR  2   /* tcgen05 contraction (bf16 bank, cosine / MSE) */
+
+typedef struct sky_bank sky_bank_t;
+
+/* Text of the last error on the calling thread. */
+SKY_API const char* sky_last_error(void);
+SKY_API int sky_abi_version(void);
+
+/* ---- bank: the device-resident, normalised embedding bank -------------------------------------
+ * Replaces the per-batch loader + token select + first-batch normalisation of mae_simsearch
+ * (utils/similarity.py:71-102): rows are normalised ONCE at upload instead of once per search.   */
+
+/* n_items bank items of L tokens x D features, stored as `dtype` tiles in HBM. */
+SKY_API int sky_bank_create(sky_bank_t** bank, int device, int64_t n_items, int L, int D, int dtype);
+SKY_API int sky_bank_destroy(sky_bank_t* bank);
+
+/* mean / unbiased std over (items, tokens) of the FIRST batch, after token selection
+ * (utils/similarity.py:98-100).  src: [n_items, src_tokens, D] of src_dtype. */
+SKY_API int sky_bank_fit_norm(sky_bank_t* bank, const void* src, int src_dtype, int64_t n_items,
+                      int src_tokens, int token_mode, int num_extra_tokens, void* stream);
+/* explicit statistics (mu[D], sigma[D]; the +1e-8 of :101-102 is added inside). */
+SKY_API int sky_bank_set_norm(sky_bank_t* bank, const float* mu, const float* sigma, void* stream);
+SKY_API int sky_bank_get_norm(const sky_bank_t* bank, float* mu, float* sigma, void* stream);
+
+/* token-select, normalise ((x-mu)/(sigma+1e-8), utils/similarity.py:102), cast and store items
+ * [item0, item0+n_items); also accumulates the per-row squared norms the tensor path needs.
+ * Without fit_norm/set_norm rows are stored un-normalised (compute_similarity semantics). */
+SKY_API int sky_bank_upload(sky_bank_t* bank, const void* src, int src_dtype, int64_t item0, int64_t n_items,
+                    int src_tokens, int token_mode, int num_extra_tokens, void* stream);
+SKY_API int sky_bank_finalize(sky_bank_t* bank, void* stream);
+/* shrink / regrow the ACTIVE item count within the capacity given at creation (a streaming caller
+ * reuses one bank for batches of varying size; get_train_samples, utils/similarity.py:4-14). */
+SKY_API int sky_bank_resize(sky_bank_t* bank, int64_t n_items);
+/* stored (normalised, rounded) rows back as f32 [n_items, L, D] -- tests / snapshots. */
+SKY_API int sky_bank_download(const sky_bank_t* bank, int64_t item0, int64_t n_items, float* dst, void* stream);
+SKY_API int sky_bank_info(const sky_bank_t* bank, int64_t* n_items, int* L, int* D, int* dtype);
+
+/* ---- query preparation ----------------------------------------------------------------------
+ * determine_target_features (utils/similarity.py:134-147) fused with the target half of the
+ * first-batch normalisation (:101): targets [T_rows, D] f32 (token-selected, flattened) ->
+ * t[D] = mean rows, w[D] = 1/std^2 normalised to sum 1 (ones if use_weights == 0, :246-247).
+ * bank may be NULL (no normalisation). */
+SKY_API int sky_query_from_targets(const sky_bank_t* bank, const float* targets, int64_t T_rows, int D,
+                           int use_weights, float* t_out, float* w_out, void* stream);
+
+/* ---- search -----------------------------------------------------------------------------------
+ * compute_similarity + update_best_scores over the whole bank (utils/similarity.py:105-110,
+ * :214-268, :18-35) for Q queries at once, with no score matrix written to HBM.
+ *  t[Q,D], w[Q,D] f32 (w NULL = ones, i.e. use_weights=False); n_top_sims 0 = None (:257-259).
+ *  out_scores[Q,k] f32 best-first, out_idx[Q,k] i64 bank item index (+ idx_offset);
+ *  when the bank has fewer than k items the tail is padded like the reference's initial fill
+ *  (:66: -inf for cosine, +inf otherwise) with index -1.  NaN scores rank as the largest value. */
+SKY_API int sky_search(sky_bank_t* bank, const float* t, const float* w, int Q, int metric, int combine,
+               int n_top_sims, int k, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+               int path, void* stream);
+/* same, host buffers in and out (pinned or pageable); H2D + D2H happen inside the call. */
+SKY_API int sky_search_host(sky_bank_t* bank, const float* h_t, const float* h_w, int Q, int metric,
+                    int combine, int n_top_sims, int k, int64_t idx_offset, float* h_out_scores,
+                    int64_t* h_out_idx, int path, void* stream);
+
+/* compute_similarity only (utils/similarity.py:214-268): scores of items [item0, item0+n_items)
+ * for Q queries -> out_scores[Q, n_items] f32.  Used by the Python mirror of compute_similarity. */
+SKY_API int sky_score(sky_bank_t* bank, const float* t, const float* w, int Q, int metric, int combine,
+              int n_top_sims, int64_t item0, int64_t n_items, float* out_scores, void* stream);
+
+/* merge R candidate lists per query into one top-k_out, best first: the shard merge after the
+ * NCCL all-gather, and the running merge of update_best_scores (utils/similarity.py:18-35).
+ * scores[R,Q,k_in] f32, idx[R,Q,k_in] i64 (idx < 0 = empty slot). */
+SKY_API int sky_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int k_out,
+                         int metric, float* out_scores, int64_t* out_idx, int device, void* stream);
+
+/* Timing of the dominant (scoring) kernel of each search with CUDA events recorded on the launch
+ * stream right around it: enable, run searches, then read (#launches, total ms); read synchronises. */
+SKY_API int sky_profile_enable(sky_bank_t* bank, int enable);
+SKY_API int sky_profile_read(sky_bank_t* bank, int64_t* launches, double* total_ms, int reset);
+
+/* kernels launched by this library on the calling thread since the last reset (bench accounting). */
+SKY_API int64_t sky_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKY_SEARCH_H_ */

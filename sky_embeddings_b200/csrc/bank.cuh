@@ -1,0 +1,98 @@
+// bank.cuh -- the bank handle and internal launcher declarations.
+#pragma once
+#include <cuda.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+struct sky_bank {
+    int device = 0;
+    int num_sms = 0;
+    int64_t n_items = 0;
+    int64_t capacity = 0;   // items allocated
+    int L = 1;          // tokens kept per item
+    int D = 0;          // feature dimension
+    int Dp = 0;         // row stride in elements (D padded to a multiple of 64)
+    int dtype = SKY_F32;
+    int64_t rows = 0;       // n_items * L
+    int64_t rows_pad = 0;   // rows rounded up to the 128-row tensor tile
+    void* data = nullptr;       // [rows_pad, Dp] row-major, normalised + rounded
+    float* rownorm = nullptr;   // [rows_pad] sum of squares of the stored row
+    float* mu = nullptr;        // [D]
+    float* sigma = nullptr;     // [D]
+    float* sp = nullptr;        // [D] sigma + 1e-8
+    bool has_norm = false;
+    bool finalized = false;
+    // grow-only scratch
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    void* ws2 = nullptr;        // small persistent scratch (query packing, statistics)
+    size_t ws2_bytes = 0;
+    // TMA descriptor of the bank (bf16 only), built at finalize
+    CUtensorMap tmap_bank;
+    bool tmap_ready = false;
+    // optional timing of the dominant (scoring) kernel: CUDA event pairs on the launch stream
+    bool profile = false;
+    std::vector<cudaEvent_t>* prof_events = nullptr;   // [2 * launches]
+};
+
+namespace sky {
+
+int ensure_ws(sky_bank* b, size_t bytes);
+int ensure_ws2(sky_bank* b, size_t bytes);
+void prof_mark(const sky_bank* b, cudaStream_t st);   // call right before and right after the scoring kernel
+
+// bank.cu
+int launch_ingest(const void* src, int src_dtype, int64_t n_items, int src_tokens, int token_mode,
+                  int num_extra, int L, int D, int Dp, const float* mu, const float* sp, void* dst,
+                  int dst_dtype, float* rownorm, int64_t dst_row0, cudaStream_t st);
+int launch_col_stats(const float* x, int64_t n_rows, int D, int ld, const float* mu_in, const float* sp_in,
+                     float* mean_out, float* std_out, cudaStream_t st);
+int launch_add_eps(const float* sigma, float* sp, int D, cudaStream_t st);
+int launch_finish_weights(const float* std_in, int D, int use_weights, float* w_out, cudaStream_t st);
+int launch_download(const void* data, int dtype, int64_t row0, int64_t nrows, int D, int Dp, float* dst,
+                    cudaStream_t st);
+
+// Search state shared by the scorers and the merge (all device memory inside bank->ws).
+struct SearchState {
+    uint64_t* lists = nullptr;   // [P][Qtot][cap]
+    int* counts = nullptr;       // [P][Qtot]
+    uint32_t* gtop = nullptr;    // [Qtot][p_stride]
+    int P = 0;                   // number of CTAs (lists) of the scorer
+    int p_stride = 0;            // P rounded up to 32
+    int Qtot = 0;
+    int cap = 0;
+    int k = 0;
+    int use_gtau = 0;
+};
+
+// simt_search.cu
+struct SimtArgs {
+    const void* bank; int dtype;
+    int64_t n_items; int L; int D; int Dp;
+    const float* t; const float* w; int Q;
+    int metric, combine, n_top;
+    // emit mode (sky_score): scores of items [item0, item0+n) -> emit[q*n + (item-item0)]
+    float* emit; int64_t item0; int64_t n;
+};
+int simt_grid(const sky_bank* b, int metric, int L, int64_t n_items, int qc, int n_top, int* grid, size_t* smem);
+int simt_pick_qc(int Dp);
+int launch_simt_search(const sky_bank* b, const SimtArgs& a, const SearchState& s, int grid, int qc, size_t smem,
+                       cudaStream_t st);
+
+// tc_search.cu
+bool tc_supported(const sky_bank* b, int metric, bool weighted, int n_top);
+int tc_grid(const sky_bank* b);
+int tc_make_bank_tmap(sky_bank* b);
+int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const SearchState& s, cudaStream_t st);
+size_t tc_scratch_bytes(const sky_bank* b, int Q);
+
+// merge.cu
+int launch_init_state(const SearchState& s, int p_active, cudaStream_t st);
+int launch_merge_lists(const SearchState& s, int metric, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                       cudaStream_t st);
+int launch_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int k_out, int metric,
+                            float* out_scores, int64_t* out_idx, cudaStream_t st);
+
+}  // namespace sky

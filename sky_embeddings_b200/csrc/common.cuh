@@ -1,0 +1,87 @@
+// common.cuh -- shared host/device definitions of libskysearch (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sky_search.h"
+
+namespace sky {
+
+constexpr int kPruneSlack = 128;   // max candidate inserts per query between two prune points
+constexpr int kTileRows = 128;     // bank rows per tensor tile (UMMA M)
+constexpr int kKBlock = 64;        // bf16 elements per 128-byte swizzle row (one TMA box / K step)
+
+// ---------------------------------------------------------------------------------------------
+// Order-preserving score keys.  A candidate is one 64-bit "composite":
+//     high 32 bits = key   (larger key = better score, NaN handled as torch.argsort does:
+//                           NaN is the LARGEST value -- first for cosine, last for MSE/MAE,
+//                           reference utils/similarity.py:24,29)
+//     low  32 bits = ~idx  (so that among equal keys the LOWER bank index wins)
+// Composite 0 never occurs for a real candidate (idx < 2^32-1), so 0 means "empty".
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t score_to_key(float s, bool largest) {
+    uint32_t o = (s != s) ? 0xFFFFFFFFu : float_to_ordered(s);
+    return largest ? o : ~o;
+}
+__host__ __device__ __forceinline__ float key_to_score(uint32_t key, bool largest) {
+    uint32_t o = largest ? key : ~key;
+    if (o == 0xFFFFFFFFu) {
+#ifdef __CUDA_ARCH__
+        return __uint_as_float(0x7FC00000u);
+#else
+        union { float f; uint32_t u; } c; c.u = 0x7FC00000u; return c.f;
+#endif
+    }
+    return ordered_to_float(o);
+}
+__host__ __device__ __forceinline__ uint64_t make_composite(uint32_t key, uint32_t idx) {
+    return (static_cast<uint64_t>(key) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
+}
+__host__ __device__ __forceinline__ uint32_t composite_key(uint64_t c) { return static_cast<uint32_t>(c >> 32); }
+__host__ __device__ __forceinline__ uint32_t composite_idx(uint64_t c) { return 0xFFFFFFFFu - static_cast<uint32_t>(c); }
+
+__host__ __device__ __forceinline__ bool metric_largest(int metric) { return metric == SKY_COSINE; }
+
+__host__ __device__ __forceinline__ int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing (api.cu owns the storage)
+// ---------------------------------------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SKY_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ::sky::set_error(SKY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,             \
+                                    cudaGetErrorString(_e), __FILE__, __LINE__);              \
+    } while (0)
+
+#define SKY_LAUNCH_CHECK(name)                                                                \
+    do {                                                                                      \
+        ::sky::count_launch();                                                                \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return ::sky::set_error(SKY_ERR_CUDA, "launch of %s failed: %s", name,            \
+                                    cudaGetErrorString(_e));                                  \
+    } while (0)
+
+}  // namespace sky

@@ -1,0 +1,169 @@
+// merge.cu -- K3/K4: merging candidate lists into the final, best-first top-k.
+//
+//  * merge_lists_kernel: per-CTA candidate lists of one scorer launch -> top-k of the shard.
+//  * merge_candidates_kernel: R (score, index) lists per query -> top-k; this is the device merge
+//    after the NCCL all-gather of per-shard results, and the running merge that replaces
+//    update_best_scores (reference utils/similarity.py:18-35: cat + argsort + [:n_save]).
+// Output padding when fewer than k candidates exist follows the reference's initial fill
+// (utils/similarity.py:66): -inf for cosine, +inf otherwise; index -1.
+#include "bank.cuh"
+#include "topk.cuh"
+
+namespace sky {
+
+constexpr int kMergeThreads = 256;
+constexpr int kPool = 4096;      // smem pool of pre-filtered candidates per query
+constexpr int kMaxK = 4096;
+
+__global__ void init_state_kernel(uint32_t* gtop, int* counts, int Qtot, int p_stride, int p_active, int P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Qtot * p_stride) gtop[i] = ((i % p_stride) < p_active) ? 0u : 0xFFFFFFFFu;
+    if (i < Qtot * P) counts[i] = 0;
+}
+
+__device__ __forceinline__ void write_result(uint64_t c, bool largest, int64_t idx_offset, float* score, int64_t* idx) {
+    if (c == 0) {
+        *score = largest ? -INFINITY : INFINITY;
+        *idx = -1;
+    } else {
+        *score = key_to_score(composite_key(c), largest);
+        *idx = static_cast<int64_t>(composite_idx(c)) + idx_offset;
+    }
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ counts,
+                   const uint32_t* __restrict__ gtop, int P, int p_stride, int Qtot, int cap, int k, int kpad,
+                   int use_gtau, int largest, int64_t idx_offset, float* __restrict__ out_scores,
+                   int64_t* __restrict__ out_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
+    uint64_t* pool = sel + kpad;                              // [kPool]
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t scratch[4];
+    __shared__ uint32_t npool;
+    __shared__ uint32_t tau_s;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kMergeThreads / 32;
+
+    if (tid == 0) { npool = 0; tau_s = 0xFFFFFFFFu; }
+    __syncthreads();
+    if (use_gtau) {
+        uint32_t lo = 0xFFFFFFFFu;
+        for (int p = tid; p < p_stride; p += kMergeThreads) lo = min(lo, gtop[static_cast<size_t>(q) * p_stride + p]);
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        if (lane == 0) atomicMin(&tau_s, lo);
+    }
+    __syncthreads();
+    // every composite with key >= tau must be kept; tau == 0 / disabled keeps everything valid
+    const uint64_t keep_ge = (use_gtau && tau_s != 0u && tau_s != 0xFFFFFFFFu) ? (static_cast<uint64_t>(tau_s) << 32) : 1ull;
+
+    for (int p = warp; p < P; p += nwarps) {
+        const int n = counts[static_cast<size_t>(p) * Qtot + q];
+        const uint64_t* e = lists + (static_cast<size_t>(p) * Qtot + q) * cap;
+        for (int i = lane; i < n; i += 32) {
+            const uint64_t v = e[i];
+            if (v >= keep_ge) {
+                const uint32_t pos = atomicAdd(&npool, 1u);
+                if (pos < kPool) pool[pos] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const int np = static_cast<int>(npool);
+    if (np <= kPool) {
+        block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch);
+    } else {
+        // rare: too many survivors (adversarial order / massive ties) -> select straight from L2
+        auto fetch = [&](int j) -> uint64_t {
+            const int p = j / cap, i = j - p * cap;
+            if (i >= counts[static_cast<size_t>(p) * Qtot + q]) return 0ull;
+            const uint64_t v = lists[(static_cast<size_t>(p) * Qtot + q) * cap + i];
+            return v >= keep_ge ? v : 0ull;
+        };
+        block_select_sort(fetch, P * cap, k, kpad, sel, hist, scratch);
+    }
+    __syncthreads();
+    for (int j = tid; j < k; j += kMergeThreads)
+        write_result(sel[j], largest != 0, idx_offset, out_scores + static_cast<size_t>(q) * k + j,
+                     out_idx + static_cast<size_t>(q) * k + j);
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_candidates_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, int R, int Q, int k_in,
+                        int k_out, int kpad, int largest, float* __restrict__ out_scores,
+                        int64_t* __restrict__ out_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t scratch[4];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int n = R * k_in;
+    // composite low word = position in the (rank-major) concatenation: lists are best-first with
+    // ties by lower index and shards hold increasing row ranges, so position order == index order
+    auto src = [&](int j) -> size_t {
+        const int r = j / k_in, i = j - r * k_in;
+        return (static_cast<size_t>(r) * Q + q) * k_in + i;
+    };
+    auto fetch = [&](int j) -> uint64_t {
+        const size_t s = src(j);
+        if (idx[s] < 0) return 0ull;
+        return make_composite(score_to_key(scores[s], largest != 0), static_cast<uint32_t>(j));
+    };
+    block_select_sort(fetch, n, k_out, kpad, sel, hist, scratch);
+    __syncthreads();
+    for (int j = tid; j < k_out; j += kMergeThreads) {
+        const uint64_t c = sel[j];
+        float* so = out_scores + static_cast<size_t>(q) * k_out + j;
+        int64_t* io = out_idx + static_cast<size_t>(q) * k_out + j;
+        if (c == 0) {
+            *so = largest ? -INFINITY : INFINITY;
+            *io = -1;
+        } else {
+            const size_t s = src(static_cast<int>(composite_idx(c)));
+            *so = scores[s];
+            *io = idx[s];
+        }
+    }
+}
+
+static int next_pow2(int v) {
+    int p = 32;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+int launch_init_state(const SearchState& s, int p_active, cudaStream_t st) {
+    const int n = s.Qtot * (s.p_stride > s.P ? s.p_stride : s.P);
+    init_state_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.gtop, s.counts, s.Qtot, s.p_stride, p_active, s.P);
+    SKY_LAUNCH_CHECK("init_state_kernel");
+    return SKY_OK;
+}
+
+int launch_merge_lists(const SearchState& s, int metric, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                       cudaStream_t st) {
+    if (s.k > kMaxK) return set_error(SKY_ERR_UNSUPPORTED, "k=%d exceeds the merge limit %d", s.k, kMaxK);
+    const int kpad = next_pow2(s.k);
+    const size_t smem = static_cast<size_t>(kpad + kPool) * sizeof(uint64_t);
+    SKY_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    merge_lists_kernel<<<s.Qtot, kMergeThreads, smem, st>>>(s.lists, s.counts, s.gtop, s.P, s.p_stride, s.Qtot, s.cap,
+                                                           s.k, kpad, s.use_gtau, metric_largest(metric) ? 1 : 0,
+                                                           idx_offset, out_scores, out_idx);
+    SKY_LAUNCH_CHECK("merge_lists_kernel");
+    return SKY_OK;
+}
+
+int launch_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int k_out, int metric,
+                            float* out_scores, int64_t* out_idx, cudaStream_t st) {
+    if (k_out > kMaxK) return set_error(SKY_ERR_UNSUPPORTED, "k=%d exceeds the merge limit %d", k_out, kMaxK);
+    if (Q == 0) return SKY_OK;
+    const int kpad = next_pow2(k_out);
+    const size_t smem = static_cast<size_t>(kpad) * sizeof(uint64_t);
+    SKY_CUDA(cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    merge_candidates_kernel<<<Q, kMergeThreads, smem, st>>>(scores, idx, R, Q, k_in, k_out, kpad,
+                                                           metric_largest(metric) ? 1 : 0, out_scores, out_idx);
+    SKY_LAUNCH_CHECK("merge_candidates_kernel");
+    return SKY_OK;
+}
+
+}  // namespace sky

@@ -1,0 +1,257 @@
+// topk.cuh -- fused top-k machinery shared by the SIMT and tcgen05 scorers and the merge kernels.
+//
+// Replaces update_best_scores (reference utils/similarity.py:18-35: cat + argsort + gather per
+// batch).  Scores never form a [Q, N] matrix in HBM:
+//   * each CTA keeps, per query, a private candidate list in L2-resident global memory, gated by a
+//     threshold held in shared memory;
+//   * the threshold is the max of (a) the CTA's own k-th best after an in-place warp radix-select
+//     prune (overflow protection) and (b) a grid-wide lower bound: every CTA publishes the best
+//     key it has seen per query; if k <= #CTAs, at least k bank rows score >= the minimum of the
+//     published keys, so anything below it can never be in the global top-k;
+//   * a final kernel merges the per-CTA lists (filter by the final bound, select, sort).
+#pragma once
+#include "common.cuh"
+
+namespace sky {
+
+__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t* p) {
+    return __ldcg(reinterpret_cast<const unsigned long long*>(p));
+}
+__device__ __forceinline__ void st_cg_u64(uint64_t* p, uint64_t v) {
+    __stcg(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg_u32(uint32_t* p, uint32_t v) { __stcg(p, v); }
+
+// ---------------------------------------------------------------------------------------------
+// Warp-level exact selection: the kth-largest (1-based) of n distinct 64-bit composites that
+// live in global memory (L2).  8 passes of 8 bits, MSB first; hist = 256 u32 of warp-private smem.
+// All 32 lanes must call; all get the result.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void radix_pick_bucket(const uint32_t* hist, int lane, int remaining,
+                                                  uint32_t& digit, uint32_t& cnt_above) {
+    // lane L owns bins [8L, 8L+8); higher lanes own higher digits
+    uint32_t c[8];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; mine += c[b]; }
+    uint32_t incl = mine;   // inclusive suffix sum over lanes
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t o = __shfl_down_sync(0xffffffffu, incl, off);
+        if (lane + off < 32) incl += o;
+    }
+    const uint32_t above = incl - mine;
+    const uint32_t rem = static_cast<uint32_t>(remaining);
+    const bool owner = (above < rem) && (rem <= above + mine);
+    uint32_t d = 0, ca = 0;
+    if (owner) {
+        uint32_t run = above;
+#pragma unroll
+        for (int b = 7; b >= 0; --b) {
+            if (run < rem && rem <= run + c[b]) { d = lane * 8 + b; ca = run; }
+            run += c[b];
+        }
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, owner);
+    const int src = __ffs(ballot) - 1;
+    digit = __shfl_sync(0xffffffffu, d, src);
+    cnt_above = __shfl_sync(0xffffffffu, ca, src);
+}
+
+__device__ __forceinline__ uint64_t warp_select_kth(const uint64_t* e, int n, int kth, uint32_t* hist) {
+    const int lane = threadIdx.x & 31;
+    uint64_t prefix = 0, mask = 0;
+    int remaining = kth;
+#pragma unroll 1
+    for (int pass = 7; pass >= 0; --pass) {
+        const int shift = pass * 8;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            uint64_t v = ld_cg_u64(e + i);
+            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 0xFF], 1u);
+        }
+        __syncwarp();
+        uint32_t digit, cnt_above;
+        radix_pick_bucket(hist, lane, remaining, digit, cnt_above);
+        remaining -= static_cast<int>(cnt_above);
+        prefix |= static_cast<uint64_t>(digit) << shift;
+        mask |= static_cast<uint64_t>(0xFF) << shift;
+        __syncwarp();
+    }
+    return prefix;
+}
+
+// Keep the entries >= thr at the front of e[0..n).  Returns the new count.
+// In-place and safe: writes always trail reads.
+__device__ __forceinline__ int warp_compact_ge(uint64_t* e, int n, uint64_t thr) {
+    const int lane = threadIdx.x & 31;
+    int out = 0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        uint64_t v = (i < n) ? ld_cg_u64(e + i) : 0;
+        bool keep = (i < n) && (v >= thr);
+        uint32_t m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) st_cg_u64(e + out + __popc(m & ((1u << lane) - 1u)), v);
+        out += __popc(m);
+        __syncwarp();
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-private candidate sink.
+// Invariant: at most kPruneSlack inserts per query happen between two calls of
+// sink_prune_if_full, and cap >= k + kPruneSlack, so a list can never overflow.
+// ---------------------------------------------------------------------------------------------
+struct Sink {
+    uint64_t* lists;   // global: [nq][cap] for this CTA
+    unsigned long long* thr;   // smem: [nq]  a candidate passes iff composite > thr
+    int* cnt;          // smem:   [nq]
+    uint32_t* lmax;    // smem:   [nq]  best key inserted so far (published grid-wide)
+    int cap;
+    int k;
+};
+
+__device__ __forceinline__ uint64_t sink_thr(const Sink& s, int q) {
+    return *reinterpret_cast<volatile unsigned long long*>(s.thr + q);
+}
+
+// Tensor-path pattern: the 32 lanes of a warp hold 32 different bank rows for the SAME query q.
+__device__ __forceinline__ void sink_insert_rows(const Sink& s, int q, bool pass, uint64_t comp) {
+    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, pass ? composite_key(comp) : 0u);
+    int base = 0;
+    if (lane == leader) {
+        base = atomicAdd(&s.cnt[q], __popc(m));
+        atomicMax(&s.lmax[q], kmax);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass) st_cg_u64(s.lists + static_cast<size_t>(q) * s.cap + base + __popc(m & ((1u << lane) - 1u)), comp);
+}
+
+// SIMT-path pattern: each calling lane owns one (item, query) pair.
+__device__ __forceinline__ void sink_insert_one(const Sink& s, int q, uint64_t comp) {
+    if (comp > sink_thr(s, q)) {
+        int pos = atomicAdd(&s.cnt[q], 1);
+        atomicMax(&s.lmax[q], composite_key(comp));
+        st_cg_u64(s.lists + static_cast<size_t>(q) * s.cap + pos, comp);
+    }
+}
+
+// One warp prunes query q down to its k best and raises the threshold.  All lanes call.
+__device__ __forceinline__ void sink_prune(const Sink& s, int q, uint32_t* hist) {
+    const int n = s.cnt[q];
+    if (n <= s.k) return;
+    uint64_t* e = s.lists + static_cast<size_t>(q) * s.cap;
+    const uint64_t kth = warp_select_kth(e, n, s.k, hist);
+    const int m = warp_compact_ge(e, n, kth);
+    if ((threadIdx.x & 31) == 0) {
+        s.cnt[q] = m;          // == k (composites are distinct)
+        atomicMax(s.thr + q, static_cast<unsigned long long>(kth));
+    }
+    __syncwarp();
+}
+
+// Called by `nwarps` warps (warp_in_group = 0..nwarps-1) between two barriers.
+__device__ __forceinline__ void sink_prune_if_full(const Sink& s, int nq, int warp_in_group, int nwarps,
+                                                   uint32_t* hist) {
+    for (int q = warp_in_group; q < nq; q += nwarps)
+        if (s.cnt[q] > s.cap - kPruneSlack) sink_prune(s, q, hist);
+}
+
+// Grid-wide bound exchange.  gtop: global [nq_total][p_stride] u32, entry (q, cta) = best key CTA
+// `cta` has inserted for query q (0 = nothing yet; slots of CTAs without work hold 0xFFFFFFFF).
+// One warp per query: publish own best, read everybody's, raise the threshold.
+__device__ __forceinline__ void sink_exchange(const Sink& s, int q, uint32_t* gtop_q, int p_stride, int cta) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        uint32_t mine = *reinterpret_cast<volatile uint32_t*>(s.lmax + q);
+        if (mine) st_cg_u32(gtop_q + cta, mine);
+    }
+    uint32_t lo = 0xFFFFFFFFu;
+    for (int p = lane; p < p_stride; p += 32) lo = min(lo, ld_cg_u32(gtop_q + p));
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    if (lane == 0 && lo != 0) {
+        // every composite with key >= lo must be kept: pass iff comp > (lo << 32) - 1
+        atomicMax(s.thr + q, (static_cast<unsigned long long>(lo) << 32) - 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-level exact top-k over a virtual array fetch(j), j in [0, n): 0 = empty entry.
+// Radix-selects the k-th largest, gathers the winners into sel[kpad] (smem, kpad = pow2 >= k),
+// bitonic-sorts them descending.  Afterwards sel[0..k) holds the result (0 = padding).
+//   hist: 256 u32 smem; scratch: 4 u32 smem.
+// ---------------------------------------------------------------------------------------------
+template <typename Fetch>
+__device__ void block_select_sort(Fetch fetch, int n, int k, int kpad, uint64_t* sel, uint32_t* hist,
+                                  uint32_t* scratch) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) { scratch[0] = 0; scratch[3] = 0; }
+    __syncthreads();
+    {
+        uint32_t local = 0;
+        for (int j = tid; j < n; j += nt) local += (fetch(j) != 0);
+        if (local) atomicAdd(&scratch[0], local);
+    }
+    __syncthreads();
+    const int total = static_cast<int>(scratch[0]);
+    uint64_t thr = 1;   // keep everything valid
+    if (total > k) {
+        uint64_t prefix = 0, mask = 0;
+        int remaining = k;
+        for (int pass = 7; pass >= 0; --pass) {
+            const int shift = pass * 8;
+            for (int b = tid; b < 256; b += nt) hist[b] = 0;
+            __syncthreads();
+            for (int j = tid; j < n; j += nt) {
+                uint64_t v = fetch(j);
+                if (v != 0 && (v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 0xFF], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                uint32_t digit, cnt_above;
+                radix_pick_bucket(hist, tid, remaining, digit, cnt_above);
+                if (tid == 0) { scratch[1] = digit; scratch[2] = cnt_above; }
+            }
+            __syncthreads();
+            remaining -= static_cast<int>(scratch[2]);
+            prefix |= static_cast<uint64_t>(scratch[1]) << shift;
+            mask |= static_cast<uint64_t>(0xFF) << shift;
+            __syncthreads();
+        }
+        thr = prefix;
+    }
+    for (int j = tid; j < kpad; j += nt) sel[j] = 0;
+    __syncthreads();
+    for (int j = tid; j < n; j += nt) {
+        uint64_t v = fetch(j);
+        if (v != 0 && v >= thr) {
+            uint32_t pos = atomicAdd(&scratch[3], 1u);
+            if (pos < static_cast<uint32_t>(kpad)) sel[pos] = v;
+        }
+    }
+    __syncthreads();
+    // bitonic sort, descending
+    for (int size = 2; size <= kpad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (kpad >> 1); i += nt) {
+                int lo = ((i / stride) * (stride << 1)) + (i % stride);
+                int hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t a = sel[lo], b = sel[hi];
+                if ((a < b) == desc) { sel[lo] = b; sel[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace sky

@@ -1,0 +1,436 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the reference's golden outputs and the
+CPU oracle on the same seeded inputs.
+
+Tolerances (north_star): scores within 1e-5 relative for fp32 banks, 1e-3 for bf16 banks, measured
+scale-relative (|a-b| <= rel * max(|ref|, max|ref|)) because cosine -> 0 makes a pure relative error
+meaningless; indices identical wherever adjacent reference gaps exceed the
+tolerance, any permutation inside a tie group.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sky_oracle as O
+from tests import golden_inputs as G
+
+pytestmark = pytest.mark.gpu
+
+REL_F32 = 1e-5
+REL_BF16 = 1e-3
+# bf16 bank vs the reference run on the ORIGINAL fp32 embeddings: here the bank's own bf16 rounding
+# (after the first-batch normalisation) is part of the difference, not only the arithmetic; with
+# D = 48 and inverse-variance weights concentrated on a few features it does not average out.
+# Every other bf16 test compares on the stored (rounded) bank values and uses REL_BF16 or tighter.
+REL_BF16_VS_F32_INPUT = 2e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from sky_embeddings_b200 import _lib
+    _lib.load()          # fail loudly if the extension is missing
+    return torch.device("cuda:0")
+
+
+def _mode(kw):
+    return "cls" if kw["cls_token"] else ("maxpool" if kw["max_pool"] else "patches")
+
+
+def _engine_simsearch(dev, bank_lat, tgt, bs, k, dtype, path="auto", **kw):
+    from sky_embeddings_b200 import Bank
+    mode = _mode(kw)
+    bank = Bank.from_latents(torch.from_numpy(bank_lat).to(dev), norm_rows=bs, token_mode=mode,
+                             num_extra_tokens=1, dtype=dtype)
+    tsel = torch.from_numpy(O.token_select(tgt, 1, kw["cls_token"], kw["max_pool"])).to(dev)
+    t, w = bank.query_from_targets(tsel, use_weights=kw["use_weights"])
+    sc, ix = bank.search(t, w if kw["use_weights"] else None, k=k, metric=kw["metric"], combine=kw["combine"], path=path)
+    out = sc[0].cpu().numpy(), ix[0].cpu().numpy()
+    bank.close()
+    return out
+
+
+@pytest.mark.parametrize("dtype,rel", [("fp32", REL_F32), ("bf16", REL_BF16_VS_F32_INPUT)])
+def test_golden_simsearch_all_modes(dev, dtype, rel):
+    g = G.load("simsearch_small")
+    bank, tgt, bs, k = G.simsearch_inputs(g)
+    for name in g["names"]:
+        kw = G.parse_simsearch_name(str(name))
+        sc, ix = _engine_simsearch(dev, bank, tgt, bs, k, dtype, **kw)
+        ref_all = None
+        if dtype == "bf16":
+            # boundary swaps between near-ties are legal at bf16 tolerance: supply all scores
+            z = O.normalise(O.token_select(bank, 1, kw["cls_token"], kw["max_pool"]),
+                            *O.first_batch_stats(O.token_select(bank, 1, kw["cls_token"], kw["max_pool"]), bs))
+            tn = O.normalise(O.token_select(tgt, 1, kw["cls_token"], kw["max_pool"]),
+                             *O.first_batch_stats(O.token_select(bank, 1, kw["cls_token"], kw["max_pool"]), bs))
+            t, w = O.target_features(tn, kw["use_weights"])
+            ref_all = O.item_scores(t, w, z, kw["metric"], kw["combine"])
+        ok, msg = O.check_topk_parity(sc, ix, g[f"scores.{name}"], g[f"idx.{name}"], rel, all_scores=ref_all)
+        assert ok, f"{dtype} {name}: {msg}"
+
+
+def test_golden_mim1_shape(dev):
+    g = G.load("simsearch_mim1_shape")
+    bank, tgt, bs, k = G.simsearch_inputs(g)
+    for metric in ("cosine", "MSE"):
+        kw = dict(metric=metric, combine="min", use_weights=True, max_pool=True, cls_token=False)
+        sc, ix = _engine_simsearch(dev, bank, tgt, bs, k, "fp32", **kw)
+        ok, msg = O.check_topk_parity(sc, ix, g[f"scores.{metric}"], g[f"idx.{metric}"], REL_F32)
+        assert ok, f"{metric}: {msg}"
+
+
+def test_short_bank_padding(dev):
+    g = G.load("short_bank")
+    bank, tgt, bs, k = G.simsearch_inputs(g)
+    n = bank.shape[0]
+    for metric in ("cosine", "MSE"):
+        kw = dict(metric=metric, combine="mean", use_weights=True, max_pool=False, cls_token=False)
+        sc, ix = _engine_simsearch(dev, bank, tgt, bs, k, "fp32", **kw)
+        ref = g[f"scores.{metric}"]
+        assert np.all(np.isinf(sc[n:])) and np.array_equal(np.sign(sc[n:]), np.sign(ref[n:]))
+        assert np.all(ix[n:] == -1)
+        ok, msg = O.check_topk_parity(sc[:n], ix[:n], ref[:n], g[f"idx.{metric}"], REL_F32)
+        assert ok, f"{metric}: {msg}"
+
+
+def test_golden_compute_similarity_mirror(dev):
+    from sky_embeddings_b200 import similarity as S
+    from sky_embeddings_b200 import synth
+    g = G.load("compute_similarity")
+    T, L, D, B, seed, s1, s2 = [int(v) for v in g["meta"]]
+    target = torch.from_numpy(synth.latents(T, L, D, seed=seed, stream=s1)).to(dev)
+    test = torch.from_numpy(synth.latents(B, L, D, seed=seed, stream=s2)).to(dev)
+    t, w = S.determine_target_features(target)
+    assert O.score_close(t.cpu().numpy(), g["t"], REL_F32).all()
+    assert O.score_close(w.cpu().numpy(), g["w"], REL_F32).all()
+    for name in g["names"]:
+        metric, combine, uw, nts = str(name).split(".")
+        s = S.compute_similarity(target, test, metric=metric, combine=combine, use_weights=(uw == "w"),
+                                 n_top_sims=None if nts == "None" else int(nts))
+        assert O.score_close(s.cpu().numpy(), g[f"scores.{name}"], REL_F32).all(), name
+    # per-token functions
+    ref = O.token_scores(g["t"].astype(np.float64), g["w"].astype(np.float64), test.cpu().numpy().astype(np.float64), "cosine")
+    got = S.weighted_cosine_similarity(t, test, w)
+    assert got.shape == (B, L) and O.score_close(got.cpu().numpy(), ref, REL_F32).all()
+    # error behaviour mirrors the reference
+    with pytest.raises(UnboundLocalError):
+        S.compute_similarity(target, test, metric="L2")
+    with pytest.raises(NameError):
+        S.compute_similarity(target, test, metric="cosine", n_central_patches=4)
+
+
+def test_golden_update_best_scores_mirror(dev):
+    from sky_embeddings_b200 import similarity as S
+    g = G.load("update_best")
+    best, new = torch.from_numpy(g["best"]).to(dev), torch.from_numpy(g["new"]).to(dev)
+    pay_b = torch.arange(4, dtype=torch.float32, device=dev).view(4, 1)
+    pay_n = torch.arange(4, 10, dtype=torch.float32, device=dev).view(6, 1)
+    ra_b = torch.stack([torch.arange(4., device=dev), torch.zeros(4, device=dev)], 1)
+    ra_n = torch.stack([torch.arange(4., 10., device=dev), torch.zeros(6, device=dev)], 1)
+    for metric in ("cosine", "MSE"):
+        b = best if metric == "cosine" else -best
+        smp, ra, sc = S.update_best_scores(pay_n, ra_n, new, pay_b, ra_b, b, 4, metric)
+        ref_s, ref_src = g[f"scores.{metric}"], g[f"src.{metric}"]
+        sc, src = sc.cpu().numpy(), ra[:, 0].cpu().numpy().astype(np.int64)
+        assert np.array_equal(np.isnan(sc), np.isnan(ref_s))
+        m = ~np.isnan(ref_s)
+        assert np.array_equal(sc[m], ref_s[m])
+        assert np.array_equal(smp[:, 0].cpu().numpy().astype(np.int64), src)      # payload follows the score
+        allv = np.r_[b.cpu().numpy(), g["new"]]
+        for j in range(4):                                                        # every pick has its own score
+            assert (np.isnan(sc[j]) and np.isnan(allv[src[j]])) or sc[j] == allv[src[j]]
+        assert len(set(src.tolist())) == 4
+
+
+class _LatentStub:
+    num_extra_tokens = 1
+
+    def eval(self):
+        return self
+
+    def forward_features(self, samples, ra_dec=None, reshape_out=False):
+        return samples, None, None
+
+
+class _Loader:
+    def __init__(self, bank, bs):
+        self.bank, self.bs = torch.as_tensor(bank), bs
+
+    def __len__(self):
+        return (self.bank.shape[0] + self.bs - 1) // self.bs
+
+    def __iter__(self):
+        n = self.bank.shape[0]
+        for s in range(0, n, self.bs):
+            e = min(n, s + self.bs)
+            ra = torch.zeros((e - s, 2))
+            ra[:, 0] = torch.arange(s, e, dtype=torch.float32)
+            yield self.bank[s:e], torch.zeros(e - s), ra
+
+
+def test_golden_mae_simsearch_mirror(dev):
+    """The reference-signature entry point, driven exactly like oracle/make_golden.py drives the reference."""
+    from sky_embeddings_b200 import similarity as S
+    g = G.load("simsearch_small")
+    bank, tgt, bs, k = G.simsearch_inputs(g)
+    for name in g["names"]:
+        kw = G.parse_simsearch_name(str(name))
+        smp, lat, ra, sc = S.mae_simsearch(_LatentStub(), torch.from_numpy(tgt), _Loader(bank, bs), dev,
+                                           nested_batches=False, n_save=k, **kw)
+        idx = ra[:, 0].cpu().numpy().astype(np.int64)
+        ok, msg = O.check_topk_parity(sc.cpu().numpy(), idx, g[f"scores.{name}"], g[f"idx.{name}"], REL_F32)
+        assert ok, f"{name}: {msg}"
+        assert np.array_equal(smp.cpu().numpy(), bank[idx]), name
+        assert lat.shape == smp.shape
+    # nested (tile) loaders: one tile holding all batches
+    kw = G.parse_simsearch_name("cosine.maxpool.min.w")
+    batches = list(_Loader(bank, bs))[:-1]          # equal-sized batches, like FitsDataset tiles
+    tile = [(torch.stack([b[0] for b in batches])[None], torch.stack([b[1] for b in batches])[None],
+             torch.stack([b[2] for b in batches])[None])]
+    smp, lat, ra, sc = S.mae_simsearch(_LatentStub(), torch.from_numpy(tgt), tile, dev, nested_batches=True,
+                                       n_save=k, **kw)
+    n_used = len(batches) * bs
+    ref_s, ref_i, *_ = O.simsearch(tgt, bank[:n_used], bs, k, **kw)
+    ok, msg = O.check_topk_parity(sc.cpu().numpy(), ra[:, 0].cpu().numpy().astype(np.int64), ref_s, ref_i, REL_F32)
+    assert ok, msg
+
+
+def _exact_model_scores(z_bf16, t, metric):
+    """What the tensor path computes, in float64: dot with the bf16-rounded query, fp32 norms."""
+    z = z_bf16.astype(np.float64)
+    tb = torch.from_numpy(t).to(torch.bfloat16).to(torch.float64).numpy()
+    dot = z @ tb.T                                   # [N, Q]
+    rn = (z ** 2).sum(1)[:, None]
+    tt = (t.astype(np.float64) ** 2).sum(1)[None, :]
+    if metric == "cosine":
+        return (dot / (np.sqrt(tt) * np.sqrt(rn) + 1e-6)).T
+    D = z.shape[1]
+    return ((tt - 2 * dot + rn) / (D * D)).T
+
+
+@pytest.mark.parametrize("metric", ["cosine", "MSE"])
+@pytest.mark.parametrize("n,Q,k", [(20000, 64, 100), (777, 5, 10), (130, 70, 100), (33000, 130, 20)])
+def test_tensor_path_vs_oracle(dev, metric, n, Q, k):
+    from sky_embeddings_b200 import Bank, synth
+    D = 768
+    lat = synth.latents(n, 1, D, stream=101)
+    bank = Bank.from_latents(torch.from_numpy(lat).to(dev), norm_rows=64, dtype="bf16")
+    z = bank.download().cpu().numpy()[:, 0]          # the stored (normalised, bf16-rounded) rows
+    rng = np.random.Generator(np.random.PCG64(5))
+    rows = rng.integers(0, n, Q)
+    t = (z[rows] + 0.3 * rng.standard_normal((Q, D))).astype(np.float32)
+    sc, ix = bank.search(torch.from_numpy(t).to(dev), None, k=k, metric=metric, path="tensor")
+    sc2, ix2 = bank.search(torch.from_numpy(t).to(dev), None, k=k, metric=metric, path="simt")
+    sc, ix, sc2, ix2 = sc.cpu().numpy(), ix.cpu().numpy(), sc2.cpu().numpy(), ix2.cpu().numpy()
+    ref_s, ref_i = O.search(t.astype(np.float64), None, z[:, None].astype(np.float64), k, metric, "min")
+    model = _exact_model_scores(z, t, metric)
+    kk = min(k, n)
+    for q in range(Q):
+        all_ref = O.item_scores(t[q].astype(np.float64), np.ones(D), z[:, None].astype(np.float64), metric, "min")
+        # fp32 SIMT path on the same stored bank: fp32 tolerance
+        ok, msg = O.check_topk_parity(sc2[q], ix2[q], ref_s[q], ref_i[q], REL_F32, all_scores=all_ref)
+        assert ok, f"simt q{q}: {msg}"
+        # tensor path: bf16 tolerance vs the oracle ...
+        ok, msg = O.check_topk_parity(sc[q], ix[q], ref_s[q], ref_i[q], REL_BF16, all_scores=all_ref)
+        assert ok, f"tensor q{q}: {msg}"
+        # ... and fp32-tight vs the exact model of what it computes (catches layout / descriptor bugs)
+        ms, mi = O.topk(model[q], k, metric)
+        ok, msg = O.check_topk_parity(sc[q], ix[q], ms, mi, 2e-5, all_scores=model[q])
+        assert ok, f"tensor-vs-model q{q}: {msg}"
+        assert np.all(ix[q][kk:] == -1)
+    bank.close()
+
+
+@pytest.mark.parametrize("dtype,rel", [("fp32", REL_F32), ("bf16", REL_F32)])
+def test_multi_query_weighted_patches(dev, dtype, rel):
+    """Q > 1 with per-query weights, L = 8 patches, every combine, n_top_sims: oracle = reference per query.
+    (bf16 bank: the oracle sees the stored values, so fp32 tolerance applies to the arithmetic.)"""
+    from sky_embeddings_b200 import Bank, synth
+    n, L, D, Q, k = 1500, 8, 96, 7, 25
+    lat = synth.latents(n, L, D, stream=111)
+    bank = Bank.from_latents(torch.from_numpy(lat).to(dev), norm_rows=32, dtype=dtype)
+    z = bank.download().cpu().numpy().astype(np.float64)
+    ts, ws = [], []
+    for q in range(Q):
+        grp = synth.target_group(z.astype(np.float32), [17 * q + 3, 29 * q + 5], copies=6, noise=0.4, stream=120 + q)
+        t, w = O.target_features(grp)
+        ts.append(t)
+        ws.append(w)
+    t = torch.from_numpy(np.stack(ts).astype(np.float32)).to(dev)
+    w = torch.from_numpy(np.stack(ws).astype(np.float32)).to(dev)
+    tn, wn = t.cpu().numpy().astype(np.float64), w.cpu().numpy().astype(np.float64)
+    for metric in ("cosine", "MSE", "MAE"):
+        for combine in ("mean", "min", "max"):
+            for nts in (None, 3):
+                sc, ix = bank.search(t, w, k=k, metric=metric, combine=combine, n_top_sims=nts)
+                ref_s, ref_i = O.search(tn, wn, z, k, metric, combine, nts)
+                for q in range(Q):
+                    ok, msg = O.check_topk_parity(sc[q].cpu().numpy(), ix[q].cpu().numpy(), ref_s[q], ref_i[q], rel)
+                    assert ok, f"{dtype} {metric}/{combine}/{nts} q{q}: {msg}"
+    bank.close()
+
+
+def test_nan_rows_and_ties(dev):
+    from sky_embeddings_b200 import Bank, synth
+    n, D, k = 400, 64, 12
+    lat = synth.latents(n, 1, D, stream=131)
+    lat[7] = np.nan
+    lat[300, 0, 5] = np.nan
+    lat[50] = lat[20]                      # exact tie: lower index must come first
+    lat[90] = lat[20]
+    t = lat[20, 0].copy()
+    for dtype in ("fp32", "bf16"):
+        bank = Bank.from_latents(torch.from_numpy(lat).to(dev), norm_rows=None, dtype=dtype)
+        z = bank.download().cpu().numpy().astype(np.float64)
+        for metric, path in (("cosine", "simt"), ("MSE", "simt"), ("cosine", "tensor"), ("MSE", "tensor")):
+            if path == "tensor" and dtype != "bf16":
+                continue
+            sc, ix = bank.search(torch.from_numpy(t).to(dev), None, k=k, metric=metric, path=path)
+            sc, ix = sc[0].cpu().numpy(), ix[0].cpu().numpy()
+            if metric == "cosine":      # NaN ranks first (torch.argsort treats NaN as the largest value)
+                assert set(ix[:2]) == {7, 300} and np.isnan(sc[:2]).all(), (dtype, metric, path, ix, sc)
+                assert ix[2:5].tolist() == [20, 50, 90], (dtype, metric, path, ix)
+            else:
+                assert ix[:3].tolist() == [20, 50, 90], (dtype, metric, path, ix)
+                assert not np.isnan(sc).any()
+        # MSE with k = n: the NaN rows come last
+        sc, ix = bank.search(torch.from_numpy(t).to(dev), None, k=n, metric="MSE", path="simt")
+        assert set(ix[0, -2:].tolist()) == {7, 300} and torch.isnan(sc[0, -2:]).all()
+        bank.close()
+
+
+@pytest.mark.parametrize("path,dtype,n", [("simt", "fp32", 400000), ("tensor", "bf16", 120000)])
+def test_adversarial_order_exercises_prune(dev, path, dtype, n):
+    """Every row beats all earlier rows: thresholds never help, lists fill and get pruned in place."""
+    from sky_embeddings_b200 import Bank
+    D, k = 64, 100
+    rng = np.random.Generator(np.random.PCG64(9))
+    t = rng.standard_normal(D).astype(np.float32)
+    e = rng.standard_normal(D).astype(np.float32)
+    scale = (1.0 + np.arange(n, 0, -1, dtype=np.float32) / 64.0)[:, None]
+    lat = (t[None, :] + scale * e[None, :]).astype(np.float32)[:, None, :]
+    bank = Bank.from_latents(torch.from_numpy(lat).to(dev), norm_rows=None, dtype=dtype)
+    z = bank.download().cpu().numpy().astype(np.float64)
+    sc, ix = bank.search(torch.from_numpy(t).to(dev), None, k=k, metric="MSE", path=path)
+    all_ref = O.item_scores(t.astype(np.float64), np.ones(D), z, "MSE", "min")
+    ref_s, ref_i = O.topk(all_ref, k, "MSE")
+    ok, msg = O.check_topk_parity(sc[0].cpu().numpy(), ix[0].cpu().numpy(), ref_s, ref_i,
+                                  REL_F32 if dtype == "fp32" else REL_BF16, all_scores=all_ref)
+    assert ok, msg
+    bank.close()
+
+
+def test_large_k_without_grid_bound(dev):
+    """k larger than the number of CTAs: the grid-wide bound is off, local prunes carry the search."""
+    from sky_embeddings_b200 import Bank, synth
+    n, D, Q, k = 30000, 128, 3, 1000
+    lat = synth.latents(n, 1, D, stream=141)
+    for dtype, path, rel in (("fp32", "simt", REL_F32), ("bf16", "tensor", REL_BF16)):
+        bank = Bank.from_latents(torch.from_numpy(lat).to(dev), norm_rows=128, dtype=dtype)
+        z = bank.download().cpu().numpy().astype(np.float64)
+        t = z[[5, 500, 5000], 0].astype(np.float32) + 0.1
+        sc, ix = bank.search(torch.from_numpy(t).to(dev), None, k=k, metric="cosine", path=path)
+        ref_s, ref_i = O.search(t.astype(np.float64), None, z, k, "cosine", "min")
+        for q in range(Q):
+            all_ref = O.item_scores(t[q].astype(np.float64), np.ones(D), z, "cosine", "min")
+            ok, msg = O.check_topk_parity(sc[q].cpu().numpy(), ix[q].cpu().numpy(), ref_s[q], ref_i[q], rel, all_scores=all_ref)
+            assert ok, f"{path} q{q}: {msg}"
+        bank.close()
+
+
+def test_merge_candidates_vs_oracle(dev):
+    from sky_embeddings_b200 import merge_candidates
+    rng = np.random.Generator(np.random.PCG64(3))
+    R, Q, kin, kout = 5, 9, 40, 64
+    for metric in ("cosine", "MSE"):
+        s = rng.standard_normal((R, Q, kin)).astype(np.float32)
+        s = -np.sort(-s, axis=2) if metric == "cosine" else np.sort(s, axis=2)
+        i = np.stack([np.stack([np.sort(rng.choice(10000, kin, replace=False)) + r * 10000 for _ in range(Q)]) for r in range(R)])
+        i[2, :, 30:] = -1                                 # a short shard
+        os_, oi = merge_candidates(torch.from_numpy(s).to(dev), torch.from_numpy(i).to(dev), kout, metric)
+        for q in range(Q):
+            ref_s, ref_i = O.merge_topk([s[r, q] for r in range(R)], [i[r, q] for r in range(R)], kout, metric)
+            assert np.array_equal(os_[q].cpu().numpy(), ref_s.astype(np.float32))
+            assert np.array_equal(oi[q].cpu().numpy(), ref_i)
+
+
+def test_sharded_equals_unsharded(dev):
+    """Emulated ranks on one GPU: shard rows, search each shard with its offset, merge candidates."""
+    from sky_embeddings_b200 import Bank, merge_candidates, shard_range, synth
+    n, D, Q, k, world = 9000, 768, 16, 50, 4
+    lat = torch.from_numpy(synth.latents(n, 1, D, stream=151)).to(dev)
+    full = Bank.from_latents(lat, norm_rows=64, dtype="bf16")
+    mu, sigma = full.norm()
+    t = full.download(0, Q)[:, 0] + 0.2
+    for metric in ("cosine", "MSE"):
+        s_full, i_full = full.search(t, None, k=k, metric=metric)
+        parts_s, parts_i = [], []
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            shard = Bank(hi - lo, 1, D, "bf16", dev).set_norm(mu, sigma)
+            shard.upload(lat[lo:hi]).finalize()
+            s, i = shard.search(t, None, k=k, metric=metric, idx_offset=lo)
+            parts_s.append(s)
+            parts_i.append(i)
+            shard.close()
+        ms, mi = merge_candidates(torch.stack(parts_s), torch.stack(parts_i), k, metric)
+        assert torch.equal(mi, i_full), metric
+        assert torch.equal(ms, s_full), metric
+    full.close()
+
+
+def test_search_host_matches_device(dev):
+    from sky_embeddings_b200 import Bank, synth
+    lat = torch.from_numpy(synth.latents(5000, 1, 768, stream=161)).to(dev)
+    bank = Bank.from_latents(lat, norm_rows=64, dtype="bf16")
+    t = bank.download(100, 64)[:, 0] + 0.1
+    s_d, i_d = bank.search(t, None, k=100, metric="cosine")
+    th = t.cpu().pin_memory()
+    s_h, i_h = bank.search_host(th, None, k=100, metric="cosine")
+    assert torch.equal(s_h, s_d.cpu()) and torch.equal(i_h, i_d.cpu())
+    bank.close()
+
+
+def test_config2_shape_property_checks(dev):
+    """BASELINE config 2 at full size (1M x 768 bf16, 64 queries, cosine top-100): planted nearest
+    neighbours, and exactness against a chunked fp32 torch scoring of the same stored bank."""
+    from sky_embeddings_b200 import Bank, synth
+    n, D, Q, k = 1_000_000, 768, 64, 100
+    bank = Bank(n, 1, D, "bf16", dev)
+    first = synth.device_bank_chunk(0, synth.CHUNK_ROWS, D, dev)
+    bank.fit_norm(first[:512])
+    for c in range((n + synth.CHUNK_ROWS - 1) // synth.CHUNK_ROWS):
+        rows = min(synth.CHUNK_ROWS, n - c * synth.CHUNK_ROWS)
+        bank.upload(synth.device_bank_chunk(c, rows, D, dev), c * synth.CHUNK_ROWS)
+    bank.finalize()
+    stride = n // Q
+    planted = [q * stride + stride // 2 for q in range(Q)]
+    gen = torch.Generator(device=dev).manual_seed(7)
+    t = torch.cat([bank.download(r, 1)[:, 0] for r in planted]) + 0.1 * torch.randn((Q, D), generator=gen, device=dev)
+    sc, ix = bank.search(t, None, k=k, metric="cosine", path="tensor")
+    assert ix[:, 0].cpu().tolist() == planted
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all())          # best first
+    # exact check against torch on the stored bank, chunked (fp32 accumulate, bf16-rounded queries)
+    tb = t.to(torch.bfloat16).to(torch.float32)
+    tt = t.pow(2).sum(1).sqrt()
+    best_s = torch.full((Q, k), float("-inf"), device=dev)
+    best_i = torch.zeros((Q, k), dtype=torch.int64, device=dev)
+    step = 1 << 17
+    for s0 in range(0, n, step):
+        z = bank.download(s0, min(step, n - s0))[:, 0]
+        s = (tb @ z.T) / (tt[:, None] * z.pow(2).sum(1).sqrt()[None, :] + 1e-6)
+        cs = torch.cat([best_s, s], 1)
+        ci = torch.cat([best_i, torch.arange(s0, s0 + z.shape[0], device=dev).expand(Q, -1)], 1)
+        best_s, o = cs.topk(k, dim=1)
+        best_i = ci.gather(1, o)
+    for q in range(Q):
+        ok, msg = O.check_topk_parity(sc[q].cpu().numpy(), ix[q].cpu().numpy(), best_s[q].cpu().numpy(),
+                                      best_i[q].cpu().numpy(), 2e-5)
+        assert ok, f"q{q}: {msg}"
+    # SIMT path on the same bank, 4 queries
+    sc2, ix2 = bank.search(t[:4], None, k=k, metric="cosine", path="simt")
+    for q in range(4):
+        ok, msg = O.check_topk_parity(sc2[q].cpu().numpy(), ix2[q].cpu().numpy(), best_s[q].cpu().numpy(),
+                                      best_i[q].cpu().numpy(), REL_BF16)
+        assert ok, f"simt q{q}: {msg}"
+    bank.close()
