@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self.window = None          # (t0, t1) of the timed region, set by the caller
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -91,7 +91,7 @@ class ClockSampler(threading.Thread):
             "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
             "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
@@ -105,7 +105,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
 
     def summary(self):
         if not self.ok or not self.samples:

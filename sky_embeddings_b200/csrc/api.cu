@@ -78,7 +78,7 @@ static int plan_state(sky_bank* b, int P, int Q, int k, int p_active, SearchStat
     s->k = k;
     // room for the k best plus one prune interval; more slack means fewer prunes
     int cap = k + kPruneSlack;
-    const int want = (k < 256) ? 512 : 2 * k + kPruneSlack;
+    const int want = (k < 256) ? 1024 : 2 * k + kPruneSlack;
     const size_t budget = static_cast<size_t>(3) << 30;
     if (static_cast<size_t>(P) * Q * want * sizeof(uint64_t) <= budget) cap = want;
     s->cap = cap;
@@ -86,12 +86,14 @@ static int plan_state(sky_bank* b, int P, int Q, int k, int p_active, SearchStat
     const size_t lists_b = static_cast<size_t>(P) * Q * cap * sizeof(uint64_t);
     const size_t counts_b = static_cast<size_t>(round_up(static_cast<int64_t>(P) * Q * sizeof(int), 256));
     const size_t gtop_b = static_cast<size_t>(round_up(static_cast<int64_t>(Q) * s->p_stride * sizeof(uint32_t), 256));
-    int rc = ensure_ws(b, lists_b + counts_b + gtop_b + 256);
+    const size_t gtau_b = static_cast<size_t>(round_up(static_cast<int64_t>(Q) * sizeof(uint32_t), 256));
+    int rc = ensure_ws(b, lists_b + counts_b + gtop_b + gtau_b + 256);
     if (rc) return rc;
     unsigned char* p = reinterpret_cast<unsigned char*>(b->ws);
     s->lists = reinterpret_cast<uint64_t*>(p);
     s->counts = reinterpret_cast<int*>(p + lists_b);
     s->gtop = reinterpret_cast<uint32_t*>(p + lists_b + counts_b);
+    s->gtau = reinterpret_cast<uint32_t*>(p + lists_b + counts_b + gtop_b);
     return SKY_OK;
 }
 

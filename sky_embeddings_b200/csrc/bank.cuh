@@ -58,7 +58,8 @@ int launch_download(const void* data, int dtype, int64_t row0, int64_t nrows, in
 struct SearchState {
     uint64_t* lists = nullptr;   // [P][Qtot][cap]
     int* counts = nullptr;       // [P][Qtot]
-    uint32_t* gtop = nullptr;    // [Qtot][p_stride]
+    uint32_t* gtop = nullptr;    // [p_stride][Qtot]  best key per (CTA, query)
+    uint32_t* gtau = nullptr;    // [Qtot]            min over CTAs, maintained by reducer CTAs
     int P = 0;                   // number of CTAs (lists) of the scorer
     int p_stride = 0;            // P rounded up to 32
     int Qtot = 0;

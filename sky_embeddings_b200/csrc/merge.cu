@@ -15,10 +15,11 @@ constexpr int kMergeThreads = 256;
 constexpr int kPool = 4096;      // smem pool of pre-filtered candidates per query
 constexpr int kMaxK = 4096;
 
-__global__ void init_state_kernel(uint32_t* gtop, int* counts, int Qtot, int p_stride, int p_active, int P) {
+__global__ void init_state_kernel(uint32_t* gtop, uint32_t* gtau, int* counts, int Qtot, int p_stride, int p_active, int P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < Qtot * p_stride) gtop[i] = ((i % p_stride) < p_active) ? 0u : 0xFFFFFFFFu;
+    if (i < Qtot * p_stride) gtop[i] = ((i / Qtot) < p_active) ? 0u : 0xFFFFFFFFu;   // [p][q]
     if (i < Qtot * P) counts[i] = 0;
+    if (i < Qtot) gtau[i] = 0u;
 }
 
 __device__ __forceinline__ void write_result(uint64_t c, bool largest, int64_t idx_offset, float* score, int64_t* idx) {
@@ -50,7 +51,7 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     __syncthreads();
     if (use_gtau) {
         uint32_t lo = 0xFFFFFFFFu;
-        for (int p = tid; p < p_stride; p += kMergeThreads) lo = min(lo, gtop[static_cast<size_t>(q) * p_stride + p]);
+        for (int p = tid; p < p_stride; p += kMergeThreads) lo = min(lo, gtop[static_cast<size_t>(p) * Qtot + q]);
         lo = __reduce_min_sync(0xffffffffu, lo);
         if (lane == 0) atomicMin(&tau_s, lo);
     }
@@ -135,7 +136,7 @@ static int next_pow2(int v) {
 
 int launch_init_state(const SearchState& s, int p_active, cudaStream_t st) {
     const int n = s.Qtot * (s.p_stride > s.P ? s.p_stride : s.P);
-    init_state_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.gtop, s.counts, s.Qtot, s.p_stride, p_active, s.P);
+    init_state_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.gtop, s.gtau, s.counts, s.Qtot, s.p_stride, p_active, s.P);
     SKY_LAUNCH_CHECK("init_state_kernel");
     return SKY_OK;
 }

@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(kSimtThreads) simt_search_kernel(const SimtPar
     float* sW = sA + QC * Dp;                                  // [QC][Dp]
     unsigned long long* sThr = reinterpret_cast<unsigned long long*>(sW + QC * Dp);   // [QC]
     float* sQc = reinterpret_cast<float*>(sThr + QC);          // [QC] cosine: |t|_w, else sum(w)
-    int* sCnt = reinterpret_cast<int*>(sQc + QC);              // [QC]
+    float* sThrF = sQc + QC;                                   // [QC] (unused by this kernel's exact test)
+    int* sCnt = reinterpret_cast<int*>(sThrF + QC);            // [QC]
     uint32_t* sLmax = reinterpret_cast<uint32_t*>(sCnt + QC);  // [QC]
     uint32_t* sHist = sLmax + QC;                              // [warps][256]
     float* sTok = reinterpret_cast<float*>(sHist + kSimtWarps * 256);   // [warps][QC][L] iff n_top
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kSimtThreads) simt_search_kernel(const SimtPar
         sA[i] = (METRIC == SKY_COSINE) ? wv * tv : tv;
         sW[i] = wv;
     }
-    if (tid < QC) { sThr[tid] = (tid < p.nq) ? 0ull : ~0ull; sCnt[tid] = 0; sLmax[tid] = 0; }
+    if (tid < QC) { sThr[tid] = (tid < p.nq) ? 0ull : ~0ull; sThrF[tid] = 0.f; sCnt[tid] = 0; sLmax[tid] = 0; }
     __syncthreads();
     if (warp < QC) {
         double acc = 0.0;
@@ -105,7 +106,8 @@ __global__ void __launch_bounds__(kSimtThreads) simt_search_kernel(const SimtPar
 
     Sink sink;
     sink.lists = p.lists ? p.lists + (static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0) * p.cap : nullptr;
-    sink.thr = sThr; sink.cnt = sCnt; sink.lmax = sLmax; sink.cap = p.cap; sink.k = p.k;
+    sink.thr = smem_addr(sThr); sink.thr_f = smem_addr(sThrF); sink.cnt = smem_addr(sCnt); sink.lmax = smem_addr(sLmax);
+    sink.cap = p.cap; sink.k = p.k; sink.largest = largest;
     const bool emit = p.emit != nullptr;
 
     const int L = p.L;
@@ -288,11 +290,17 @@ __global__ void __launch_bounds__(kSimtThreads) simt_search_kernel(const SimtPar
 
         if (!emit && ((round + 1) % check_every == 0)) {
             __syncthreads();
-            sink_prune_if_full(sink, p.nq, warp, kSimtWarps, sHist + warp * 256);
+            sink_prune_if_full(sink, p.nq, warp, kSimtWarps, smem_addr(sHist + warp * 256));
             // exchange the grid-wide bound often early on, then at a decaying rate
             if (p.use_gtau && (check_idx < 8 || (check_idx & (check_idx - 1)) == 0 || (check_idx & 15) == 0))
-                for (int q = warp; q < p.nq; q += kSimtWarps)
-                    sink_exchange(sink, q, p.gtop + static_cast<size_t>(p.q0 + q) * p.p_stride, p.p_stride, blockIdx.x);
+            {
+                // gtop is [cta][query]: publish this CTA's row, then min over CTAs per query column
+                if (warp == kSimtWarps - 1) exchange_publish(sink, p.nq, p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0);
+                for (int q = warp; q < p.nq; q += kSimtWarps) {
+                    const uint32_t lo = exchange_reduce(p.gtop + p.q0 + q, p.p_stride, p.Qtot);
+                    if (lane == 0) exchange_apply(sink, q, lo);
+                }
+            }
             ++check_idx;
             __syncthreads();
         }
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(kSimtThreads) simt_search_kernel(const SimtPar
         for (int q = warp; q < p.nq; q += kSimtWarps) {
             if (lane == 0) {
                 p.counts[static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q] = sCnt[q];
-                if (p.use_gtau && sLmax[q]) st_cg_u32(p.gtop + static_cast<size_t>(p.q0 + q) * p.p_stride + blockIdx.x, sLmax[q]);
+                if (p.use_gtau && sLmax[q]) st_cg_u32(p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q, sLmax[q]);
             }
         }
     }
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(kSimtThreads) simt_search_kernel(const SimtPar
 // ---------------------------------------------------------------------------------------------
 static size_t simt_smem_bytes(int Dp, int qc, int L, int n_top) {
     size_t b = static_cast<size_t>(2) * qc * Dp * sizeof(float);
-    b += qc * (sizeof(unsigned long long) + sizeof(float) + sizeof(int) + sizeof(uint32_t));
+    b += qc * (sizeof(unsigned long long) + 2 * sizeof(float) + sizeof(int) + sizeof(uint32_t));
     b += kSimtWarps * 256 * sizeof(uint32_t);
     if (n_top > 0) b += static_cast<size_t>(kSimtWarps) * qc * L * sizeof(float);
     return (b + 15) / 16 * 16;

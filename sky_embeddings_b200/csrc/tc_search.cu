@@ -27,7 +27,7 @@ constexpr int kMaxStages = 8;
 struct TcParams {
     const float* rownorm;   // [rows_pad]
     const float* qconst;    // [BN] cosine: |t| ; MSE: |t|^2
-    uint64_t* lists; int* counts; uint32_t* gtop;
+    uint64_t* lists; int* counts; uint32_t* gtop; uint32_t* gtau;
     int p_stride, Qtot, q0, nq, cap, k, use_gtau;
     int64_t rows;           // valid bank rows
     int num_tiles, kblocks, stages, metric;
@@ -52,7 +52,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
     uint64_t* tmem_empty = tmem_full + 2;                       // [2]
     unsigned long long* sThr = reinterpret_cast<unsigned long long*>(tmem_empty + 2);   // [BN]
     float* sQc = reinterpret_cast<float*>(sThr + BN);           // [BN]
-    int* sCnt = reinterpret_cast<int*>(sQc + BN);               // [BN]
+    float* sThrF = sQc + BN;                                    // [BN] threshold as a score (pre-filter)
+    int* sCnt = reinterpret_cast<int*>(sThrF + BN);             // [BN]
     uint32_t* sLmax = reinterpret_cast<uint32_t*>(sCnt + BN);   // [BN]
     uint32_t* sHist = sLmax + BN;                               // [4][256]
     uint32_t* sTmemBase = sHist + 4 * 256;                      // [1]
@@ -81,6 +82,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
     }
     for (int q = tid; q < BN; q += kTcThreads) {
         sThr[q] = (q < p.nq) ? 0ull : ~0ull;
+        sThrF[q] = __uint_as_float(0x7FC00000u);   // NaN: the pre-filter lets everything through
         sQc[q] = p.qconst[q];
         sCnt[q] = 0;
         sLmax[q] = 0;
@@ -92,7 +94,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
 
     Sink sink;
     sink.lists = p.lists + (static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0) * p.cap;
-    sink.thr = sThr; sink.cnt = sCnt; sink.lmax = sLmax; sink.cap = p.cap; sink.k = p.k;
+    sink.thr = smem_addr(sThr); sink.thr_f = smem_addr(sThrF); sink.cnt = smem_addr(sCnt); sink.lmax = smem_addr(sLmax);
+    sink.cap = p.cap; sink.k = p.k; sink.largest = largest;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -148,7 +151,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
         // ===================== epilogue =====================
         const int e = warp - kEpiWarp0;
         const int quarter = warp & 3;                          // TMEM lanes this warp may access
-        uint32_t* hist = sHist + e * 256;
+        const uint32_t hist = smem_addr(sHist + e * 256);
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int acc = it & 1;
@@ -171,13 +174,30 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
             const uint32_t ridx = static_cast<uint32_t>(row);
 #pragma unroll
             for (int q = 0; q < BN; ++q) {
-                const float dot = __uint_as_float(v[q]);
-                float s;
-                if (largest) s = dot / (sQc[q] * mx + 1e-6f);
-                else s = (sQc[q] - 2.0f * dot + rn) * p.inv_dd;
-                const uint64_t comp = make_composite(score_to_key(s, largest), ridx);
-                const bool pass = valid && (comp > sink_thr(sink, q));
-                sink_insert_rows(sink, q, pass, comp);
+                if (q < p.nq) {                                  // warp-uniform
+                    const float dot = __uint_as_float(v[q]);
+                    const float thf = sink_thr_score(sink, q);
+                    // cheap, conservative pre-filter in the space of the accumulator: no division,
+                    // no key; NaN always goes on to the exact test (NaN ranks first for cosine)
+                    float den = 0.f, s = 0.f;
+                    bool maybe;
+                    if (largest) {
+                        den = fmaf(sQc[q], mx, 1e-6f);
+                        float bound = thf * den;
+                        bound = fmaf(-fabsf(bound), 1e-6f, bound);
+                        maybe = !(dot < bound);
+                    } else {
+                        s = (sQc[q] - 2.0f * dot + rn) * p.inv_dd;
+                        maybe = !(s > thf);
+                    }
+                    maybe = maybe && valid;
+                    if (__any_sync(0xffffffffu, maybe)) {
+                        if (largest) s = dot / den;
+                        const uint64_t comp = make_composite(score_to_key(s, largest), ridx);
+                        const bool pass = maybe && (comp > sink_thr(sink, q));
+                        sink_insert_rows(sink, q, pass, comp);
+                    }
+                }
             }
             ptx::named_bar_sync(1, kEpiThreads);
             sink_prune_if_full(sink, p.nq, e, 4, hist);
@@ -185,27 +205,27 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
             if (e == 0 && lane == 0) *sTilesDone = it + 1;
         }
         // final: counts and the last published bound
-        for (int q = e; q < p.nq; q += 4) {
-            if (lane == 0) {
-                p.counts[static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q] = sCnt[q];
-                if (p.use_gtau && sLmax[q])
-                    st_cg_u32(p.gtop + static_cast<size_t>(p.q0 + q) * p.p_stride + blockIdx.x, sLmax[q]);
-            }
+        ptx::named_bar_sync(1, kEpiThreads);
+        for (int q = e * 32 + lane; q < p.nq; q += 128) {
+            p.counts[static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q] = static_cast<int>(lds_u32(sink.cnt + q * 4));
+            const uint32_t mine = lds_u32(sink.lmax + q * 4);
+            if (p.use_gtau && mine) st_cg_u32(p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q, mine);
         }
     } else {
         // ===================== threshold exchange =====================
+        // publish this CTA's best keys, reduce one query column for everybody, apply all bounds;
+        // runs free of the epilogue (all state is monotone), fast at first, then at a trickle
         if (p.use_gtau && my_tiles > 0) {
-            int next = 1;
-            while (true) {
-                const int done = *sTilesDone;
-                if (done >= my_tiles) break;
-                if (done >= next) {
-                    for (int q = 0; q < p.nq; ++q)
-                        sink_exchange(sink, q, p.gtop + static_cast<size_t>(p.q0 + q) * p.p_stride, p.p_stride, blockIdx.x);
-                    next = (done < 4) ? done + 1 : done + (done >> 1);
-                } else {
-                    __nanosleep(500);
-                }
+            uint32_t* my_row = p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0;
+            const int rq = static_cast<int>(blockIdx.x) % p.nq;
+            int round = 0;
+            while (*sTilesDone < my_tiles) {
+                exchange_publish(sink, p.nq, my_row);
+                const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot);
+                if (lane == 0 && lo != 0u) atomicMax(p.gtau + p.q0 + rq, lo);
+                for (int q = lane; q < p.nq; q += 32) exchange_apply(sink, q, ld_cg_u32(p.gtau + p.q0 + q));
+                ++round;
+                __nanosleep(round < 24 ? 100 : 3000);
             }
         }
     }
@@ -279,7 +299,7 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, i
 constexpr int kTcBN = 64;
 
 static size_t tc_tail_bytes(int BN) {
-    return (2 * kMaxStages + 1 + 4) * sizeof(uint64_t) + BN * (8 + 4 + 4 + 4) + 4 * 256 * 4 + 16;
+    return (2 * kMaxStages + 1 + 4) * sizeof(uint64_t) + BN * (8 + 4 + 4 + 4 + 4) + 4 * 256 * 4 + 16;
 }
 
 static int tc_stages(int Dp, int BN) {
@@ -335,7 +355,7 @@ int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const Searc
         TcParams p;
         p.rownorm = b->rownorm;
         p.qconst = qconst + q0;
-        p.lists = s.lists; p.counts = s.counts; p.gtop = s.gtop;
+        p.lists = s.lists; p.counts = s.counts; p.gtop = s.gtop; p.gtau = s.gtau;
         p.p_stride = s.p_stride; p.Qtot = s.Qtot; p.q0 = q0; p.nq = (Q - q0 < BN) ? (Q - q0) : BN;
         p.cap = s.cap; p.k = s.k; p.use_gtau = s.use_gtau;
         p.rows = b->rows;

@@ -24,17 +24,40 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg
 __device__ __forceinline__ void st_cg_u32(uint32_t* p, uint32_t v) { __stcg(p, v); }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-level exact selection: the kth-largest (1-based) of n distinct 64-bit composites that
-// live in global memory (L2).  8 passes of 8 bits, MSB first; hist = 256 u32 of warp-private smem.
-// All 32 lanes must call; all get the result.
+// explicit shared-memory accessors (32-bit shared-window addresses): the sink state is reached
+// through structs, where the compiler would otherwise fall back to slow generic LD/ST/ATOM
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void radix_pick_bucket(const uint32_t* hist, int lane, int remaining,
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a) {
+    uint64_t v; asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v; asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_add_u32(uint32_t a, uint32_t v) {
+    uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o;
+}
+__device__ __forceinline__ void reds_add_u32(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_max_u32(uint32_t a, uint32_t v) { asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_max_u64(uint32_t a, uint64_t v) { asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// Warp-level exact selection: the kth-largest (1-based) of n distinct 64-bit composites that
+// live in global memory (L2).  8 passes of 8 bits, MSB first; hist = 256 u32 of warp-private smem
+// (shared-window address).  All 32 lanes must call; all get the result.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void radix_pick_bucket(uint32_t hist, int lane, int remaining,
                                                   uint32_t& digit, uint32_t& cnt_above) {
     // lane L owns bins [8L, 8L+8); higher lanes own higher digits
     uint32_t c[8];
     uint32_t mine = 0;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; mine += c[b]; }
+    for (int b = 0; b < 8; ++b) { c[b] = lds_u32(hist + (lane * 8 + b) * 4); mine += c[b]; }
     uint32_t incl = mine;   // inclusive suffix sum over lanes
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -59,7 +82,7 @@ __device__ __forceinline__ void radix_pick_bucket(const uint32_t* hist, int lane
     cnt_above = __shfl_sync(0xffffffffu, ca, src);
 }
 
-__device__ __forceinline__ uint64_t warp_select_kth(const uint64_t* e, int n, int kth, uint32_t* hist) {
+__device__ __forceinline__ uint64_t warp_select_kth(const uint64_t* e, int n, int kth, uint32_t hist) {
     const int lane = threadIdx.x & 31;
     uint64_t prefix = 0, mask = 0;
     int remaining = kth;
@@ -67,11 +90,11 @@ __device__ __forceinline__ uint64_t warp_select_kth(const uint64_t* e, int n, in
     for (int pass = 7; pass >= 0; --pass) {
         const int shift = pass * 8;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+        for (int b = 0; b < 8; ++b) sts_u32(hist + (lane * 8 + b) * 4, 0u);
         __syncwarp();
         for (int i = lane; i < n; i += 32) {
             uint64_t v = ld_cg_u64(e + i);
-            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 0xFF], 1u);
+            if ((v & mask) == prefix) reds_add_u32(hist + static_cast<uint32_t>((v >> shift) & 0xFF) * 4, 1u);
         }
         __syncwarp();
         uint32_t digit, cnt_above;
@@ -103,21 +126,31 @@ __device__ __forceinline__ int warp_compact_ge(uint64_t* e, int n, uint64_t thr)
 }
 
 // ---------------------------------------------------------------------------------------------
-// CTA-private candidate sink.
+// CTA-private candidate sink.  Shared-memory state is addressed through the shared window.
 // Invariant: at most kPruneSlack inserts per query happen between two calls of
 // sink_prune_if_full, and cap >= k + kPruneSlack, so a list can never overflow.
 // ---------------------------------------------------------------------------------------------
 struct Sink {
     uint64_t* lists;   // global: [nq][cap] for this CTA
-    unsigned long long* thr;   // smem: [nq]  a candidate passes iff composite > thr
-    int* cnt;          // smem:   [nq]
-    uint32_t* lmax;    // smem:   [nq]  best key inserted so far (published grid-wide)
+    uint32_t thr;      // smem u64[nq]: a candidate passes iff composite > thr
+    uint32_t thr_f;    // smem f32[nq]: the threshold as a score, for the cheap pre-filter
+    uint32_t cnt;      // smem u32[nq]
+    uint32_t lmax;     // smem u32[nq]: best key inserted so far (published grid-wide)
     int cap;
     int k;
+    bool largest;
 };
 
-__device__ __forceinline__ uint64_t sink_thr(const Sink& s, int q) {
-    return *reinterpret_cast<volatile unsigned long long*>(s.thr + q);
+__device__ __forceinline__ uint64_t sink_thr(const Sink& s, int q) { return lds_u64(s.thr + q * 8); }
+__device__ __forceinline__ float sink_thr_score(const Sink& s, int q) { return lds_f32(s.thr_f + q * 4); }
+
+// Raise the threshold of query q to composite `c` (monotone; callable concurrently).
+__device__ __forceinline__ void sink_raise(const Sink& s, int q, uint64_t c) {
+    reds_max_u64(s.thr + q * 8, c);
+    // the float mirror may lag or be slightly stale: it only gates the pre-filter, which is
+    // conservative, and the exact composite compare decides.  Benign race: values only tighten.
+    const uint64_t now = lds_u64(s.thr + q * 8);
+    sts_f32(s.thr_f + q * 4, key_to_score(composite_key(now), s.largest));
 }
 
 // Tensor-path pattern: the 32 lanes of a warp hold 32 different bank rows for the SAME query q.
@@ -127,10 +160,10 @@ __device__ __forceinline__ void sink_insert_rows(const Sink& s, int q, bool pass
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(m) - 1;
     const uint32_t kmax = __reduce_max_sync(0xffffffffu, pass ? composite_key(comp) : 0u);
-    int base = 0;
+    uint32_t base = 0;
     if (lane == leader) {
-        base = atomicAdd(&s.cnt[q], __popc(m));
-        atomicMax(&s.lmax[q], kmax);
+        base = atoms_add_u32(s.cnt + q * 4, __popc(m));
+        reds_max_u32(s.lmax + q * 4, kmax);
     }
     base = __shfl_sync(0xffffffffu, base, leader);
     if (pass) st_cg_u64(s.lists + static_cast<size_t>(q) * s.cap + base + __popc(m & ((1u << lane) - 1u)), comp);
@@ -139,49 +172,59 @@ __device__ __forceinline__ void sink_insert_rows(const Sink& s, int q, bool pass
 // SIMT-path pattern: each calling lane owns one (item, query) pair.
 __device__ __forceinline__ void sink_insert_one(const Sink& s, int q, uint64_t comp) {
     if (comp > sink_thr(s, q)) {
-        int pos = atomicAdd(&s.cnt[q], 1);
-        atomicMax(&s.lmax[q], composite_key(comp));
+        const uint32_t pos = atoms_add_u32(s.cnt + q * 4, 1u);
+        reds_max_u32(s.lmax + q * 4, composite_key(comp));
         st_cg_u64(s.lists + static_cast<size_t>(q) * s.cap + pos, comp);
     }
 }
 
 // One warp prunes query q down to its k best and raises the threshold.  All lanes call.
-__device__ __forceinline__ void sink_prune(const Sink& s, int q, uint32_t* hist) {
-    const int n = s.cnt[q];
+__device__ __forceinline__ void sink_prune(const Sink& s, int q, uint32_t hist) {
+    const int n = static_cast<int>(lds_u32(s.cnt + q * 4));
     if (n <= s.k) return;
     uint64_t* e = s.lists + static_cast<size_t>(q) * s.cap;
     const uint64_t kth = warp_select_kth(e, n, s.k, hist);
     const int m = warp_compact_ge(e, n, kth);
     if ((threadIdx.x & 31) == 0) {
-        s.cnt[q] = m;          // == k (composites are distinct)
-        atomicMax(s.thr + q, static_cast<unsigned long long>(kth));
+        sts_u32(s.cnt + q * 4, static_cast<uint32_t>(m));   // == k (composites are distinct)
+        sink_raise(s, q, kth);
     }
     __syncwarp();
 }
 
 // Called by `nwarps` warps (warp_in_group = 0..nwarps-1) between two barriers.
 __device__ __forceinline__ void sink_prune_if_full(const Sink& s, int nq, int warp_in_group, int nwarps,
-                                                   uint32_t* hist) {
+                                                   uint32_t hist) {
     for (int q = warp_in_group; q < nq; q += nwarps)
-        if (s.cnt[q] > s.cap - kPruneSlack) sink_prune(s, q, hist);
+        if (static_cast<int>(lds_u32(s.cnt + q * 4)) > s.cap - kPruneSlack) sink_prune(s, q, hist);
 }
 
-// Grid-wide bound exchange.  gtop: global [nq_total][p_stride] u32, entry (q, cta) = best key CTA
-// `cta` has inserted for query q (0 = nothing yet; slots of CTAs without work hold 0xFFFFFFFF).
-// One warp per query: publish own best, read everybody's, raise the threshold.
-__device__ __forceinline__ void sink_exchange(const Sink& s, int q, uint32_t* gtop_q, int p_stride, int cta) {
+// ---------------------------------------------------------------------------------------------
+// Grid-wide bound exchange.
+//   gtop [p_stride][Qtot] u32: row p = best key CTA p has inserted per query (0 = nothing yet; rows
+//                              of CTAs without work hold 0xFFFFFFFF)
+//   gtau [Qtot] u32:           min over p of gtop[p][q], maintained by designated reducer CTAs
+// If k <= #CTAs with work, at least k bank rows have key >= gtau[q], so a candidate with a smaller
+// key can never be in the global top-k.  All values only grow; every race is benign.
+// ---------------------------------------------------------------------------------------------
+// publish this CTA's best keys for queries [0, nq) (one warp)
+__device__ __forceinline__ void exchange_publish(const Sink& s, int nq, uint32_t* gtop_row) {
+    for (int q = threadIdx.x & 31; q < nq; q += 32) {
+        const uint32_t mine = lds_u32(s.lmax + q * 4);
+        if (mine) st_cg_u32(gtop_row + q, mine);
+    }
+}
+// one warp: min over CTAs of query column q  ->  gtau
+__device__ __forceinline__ uint32_t exchange_reduce(const uint32_t* gtop_col, int p_stride, int q_stride) {
     const int lane = threadIdx.x & 31;
-    if (lane == 0) {
-        uint32_t mine = *reinterpret_cast<volatile uint32_t*>(s.lmax + q);
-        if (mine) st_cg_u32(gtop_q + cta, mine);
-    }
     uint32_t lo = 0xFFFFFFFFu;
-    for (int p = lane; p < p_stride; p += 32) lo = min(lo, ld_cg_u32(gtop_q + p));
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    if (lane == 0 && lo != 0) {
-        // every composite with key >= lo must be kept: pass iff comp > (lo << 32) - 1
-        atomicMax(s.thr + q, (static_cast<unsigned long long>(lo) << 32) - 1ull);
-    }
+    for (int p = lane; p < p_stride; p += 32) lo = min(lo, ld_cg_u32(gtop_col + static_cast<size_t>(p) * q_stride));
+    return __reduce_min_sync(0xffffffffu, lo);
+}
+// raise the local threshold of query q to the grid-wide bound `lo` (a key; 0 = no information)
+__device__ __forceinline__ void exchange_apply(const Sink& s, int q, uint32_t lo) {
+    // every composite with key >= lo must be kept: pass iff comp > (lo << 32) - 1
+    if (lo != 0u) sink_raise(s, q, (static_cast<uint64_t>(lo) << 32) - 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -218,7 +261,7 @@ __device__ void block_select_sort(Fetch fetch, int n, int k, int kpad, uint64_t*
             __syncthreads();
             if (tid < 32) {
                 uint32_t digit, cnt_above;
-                radix_pick_bucket(hist, tid, remaining, digit, cnt_above);
+                radix_pick_bucket(smem_addr(hist), tid, remaining, digit, cnt_above);
                 if (tid == 0) { scratch[1] = digit; scratch[2] = cnt_above; }
             }
             __syncthreads();
