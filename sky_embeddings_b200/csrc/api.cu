@@ -146,10 +146,11 @@ int sky_bank_create(sky_bank_t** out, int device, int64_t n_items, int L, int D,
     }
     b->sigma = b->mu + D;
     b->sp = b->sigma + D;
-    // pad rows (and pad columns of the last tile) must be finite zeros for the tensor path
+    // the pad rows of the last tile must be finite zeros for the tensor path: clear that tile
     const size_t pad_rows = static_cast<size_t>(b->rows_pad - b->rows);
     if (pad_rows) {
-        cudaMemset(reinterpret_cast<unsigned char*>(b->data) + static_cast<size_t>(b->rows) * b->Dp * esz, 0, pad_rows * b->Dp * esz);
+        const size_t tile_elems = static_cast<size_t>(kTileRows) * b->Dp;
+        cudaMemset(reinterpret_cast<unsigned char*>(b->data) + (data_b - tile_elems * esz), 0, tile_elems * esz);
         cudaMemset(b->rownorm + b->rows, 0, pad_rows * sizeof(float));
     }
     *out = b;
@@ -191,8 +192,8 @@ int sky_bank_fit_norm(sky_bank_t* b, const void* src, int src_dtype, int64_t n_i
     DeviceGuard g(b->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t nrows = n_items * b->L;
-    // token-selected first batch as f32 [nrows, Dp] (+ throw-away row norms)
-    const size_t tmp_b = static_cast<size_t>(nrows) * b->Dp * sizeof(float);
+    // token-selected first batch as f32 tiles (+ throw-away row norms)
+    const size_t tmp_b = static_cast<size_t>(round_up(nrows, kTileRows)) * b->Dp * sizeof(float);
     int rc = ensure_ws2(b, tmp_b + static_cast<size_t>(nrows) * sizeof(float) + 256);
     if (rc) return rc;
     float* tmp = reinterpret_cast<float*>(b->ws2);
@@ -200,7 +201,7 @@ int sky_bank_fit_norm(sky_bank_t* b, const void* src, int src_dtype, int64_t n_i
     rc = launch_ingest(src, src_dtype, n_items, src_tokens, token_mode, num_extra_tokens, b->L, b->D, b->Dp,
                        nullptr, nullptr, tmp, SKY_F32, tmp_norm, 0, st);
     if (rc) return rc;
-    rc = launch_col_stats(tmp, nrows, b->D, b->Dp, nullptr, nullptr, b->mu, b->sigma, st);
+    rc = launch_col_stats(tmp, nrows, b->D, b->Dp, b->Dp / kKBlock, nullptr, nullptr, b->mu, b->sigma, st);
     if (rc) return rc;
     rc = launch_add_eps(b->sigma, b->sp, b->D, st);
     if (rc) return rc;
@@ -257,6 +258,9 @@ int sky_bank_finalize(sky_bank_t* b, void* stream) {
     return SKY_OK;
 }
 
+/* debug only (not part of the public header): timeline of the tensor kernel, see tc_search.cu */
+__attribute__((visibility("default"))) int sky_debug_trace(unsigned long long* h_out, int n) { return debug_read_trace(h_out, n); }
+
 int sky_profile_enable(sky_bank_t* b, int enable) {
     if (!b) return set_error(SKY_ERR_ARG, "bank is NULL");
     if (!b->prof_events) b->prof_events = new std::vector<cudaEvent_t>();
@@ -310,7 +314,7 @@ int sky_query_from_targets(const sky_bank_t* b, const float* targets, int64_t T_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool nrm = b && b->has_norm;
     // std goes to w_out first, then is turned into weights in place
-    int rc = launch_col_stats(targets, T_rows, D, D, nrm ? b->mu : nullptr, nrm ? b->sp : nullptr, t_out, w_out, st);
+    int rc = launch_col_stats(targets, T_rows, D, D, 0, nrm ? b->mu : nullptr, nrm ? b->sp : nullptr, t_out, w_out, st);
     if (rc) return rc;
     return launch_finish_weights(w_out, D, use_weights, w_out, st);
 }
@@ -352,7 +356,7 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
         rc = launch_init_state(s, grid, st);
         if (rc) return rc;
         SimtArgs a;
-        a.bank = b->data; a.dtype = b->dtype; a.n_items = b->n_items; a.L = b->L; a.D = b->D; a.Dp = b->Dp;
+        a.bank = b->data; a.dtype = b->dtype; a.row0 = 0; a.n_items = b->n_items; a.L = b->L; a.D = b->D; a.Dp = b->Dp;
         a.t = t; a.w = w; a.Q = Q; a.metric = metric; a.combine = combine; a.n_top = n_top_sims;
         a.emit = nullptr; a.item0 = 0; a.n = 0;
         rc = launch_simt_search(b, a, s, grid, qc, smem, st);
@@ -413,9 +417,8 @@ int sky_score(sky_bank_t* b, const float* t, const float* w, int Q, int metric, 
     size_t smem = 0;
     int rc = simt_grid(b, metric, b->L, n_items, qc, n_top_sims, &grid, &smem);
     if (rc) return rc;
-    const size_t esz = b->dtype == SKY_BF16 ? 2 : 4;
     SimtArgs a;
-    a.bank = reinterpret_cast<const unsigned char*>(b->data) + static_cast<size_t>(item0) * b->L * b->Dp * esz;
+    a.bank = b->data; a.row0 = item0 * b->L;
     a.dtype = b->dtype; a.n_items = n_items; a.L = b->L; a.D = b->D; a.Dp = b->Dp;
     a.t = t; a.w = w; a.Q = Q; a.metric = metric; a.combine = combine; a.n_top = n_top_sims;
     a.emit = out_scores; a.item0 = 0; a.n = n_items;

@@ -17,7 +17,7 @@ __device__ __forceinline__ float max_nan(float a, float b) {
     return (a != a || b != b) ? __uint_as_float(0x7FC00000u) : fmaxf(a, b);
 }
 
-// One warp per output row.  dst row stride = Dp elements; columns [D, Dp) are zero-filled.
+// One warp per output row, written in the tile-major layout; columns [D, Dp) are zero-filled.
 template <typename BankT>
 __global__ void ingest_kernel(const void* __restrict__ src, int src_dtype, int64_t n_items, int src_tokens,
                               int token_mode, int num_extra, int L, int D, int Dp,
@@ -34,7 +34,7 @@ __global__ void ingest_kernel(const void* __restrict__ src, int src_dtype, int64
     if (token_mode == SKY_TOK_CLS) tok0 = 0;
     else if (token_mode == SKY_TOK_PATCHES) tok0 = num_extra + l;
     else if (token_mode == SKY_TOK_MAXPOOL) { tok0 = num_extra; ntok = src_tokens - num_extra; }
-    BankT* out = dst + static_cast<size_t>(dst_row0 + warp) * Dp;
+    BankT* out = dst + tile_row_base(dst_row0 + warp, Dp / kKBlock);
     float ss = 0.f;
     for (int d = lane; d < Dp; d += 32) {
         float z = 0.f;
@@ -47,10 +47,10 @@ __global__ void ingest_kernel(const void* __restrict__ src, int src_dtype, int64
         float stored;
         if constexpr (sizeof(BankT) == 2) {
             __nv_bfloat16 b = __float2bfloat16_rn(z);
-            out[d] = b;
+            out[tile_col_off(d)] = b;
             stored = __bfloat162float(b);
         } else {
-            out[d] = z;
+            out[tile_col_off(d)] = z;
             stored = z;
         }
         ss = fmaf(stored, stored, ss);
@@ -63,7 +63,7 @@ __global__ void ingest_kernel(const void* __restrict__ src, int src_dtype, int64
 // Column statistics over rows: mean and unbiased std (two passes, fp64 accumulation).
 // Optional on-the-fly normalisation of the input with (mu_in, sp_in).
 // grid = ceil(D/32), block = (32, 8).
-__global__ void col_stats_kernel(const float* __restrict__ x, int64_t n_rows, int D, int ld,
+__global__ void col_stats_kernel(const float* __restrict__ x, int64_t n_rows, int D, int ld, int tiled_kblocks,
                                  const float* __restrict__ mu_in, const float* __restrict__ sp_in,
                                  float* __restrict__ mean_out, float* __restrict__ std_out) {
     __shared__ double red[8][33];
@@ -75,7 +75,7 @@ __global__ void col_stats_kernel(const float* __restrict__ x, int64_t n_rows, in
     double s = 0.0;
     if (ok)
         for (int64_t r = threadIdx.y; r < n_rows; r += 8) {
-            float v = x[static_cast<size_t>(r) * ld + d];
+            float v = tiled_kblocks ? x[tile_offset(r, d, tiled_kblocks)] : x[static_cast<size_t>(r) * ld + d];
             if (nrm) v = (v - m_in) / s_in;
             s += static_cast<double>(v);
         }
@@ -88,7 +88,7 @@ __global__ void col_stats_kernel(const float* __restrict__ x, int64_t n_rows, in
     double ss = 0.0;
     if (ok)
         for (int64_t r = threadIdx.y; r < n_rows; r += 8) {
-            float v = x[static_cast<size_t>(r) * ld + d];
+            float v = tiled_kblocks ? x[tile_offset(r, d, tiled_kblocks)] : x[static_cast<size_t>(r) * ld + d];
             if (nrm) v = (v - m_in) / s_in;
             double dv = static_cast<double>(v) - mean;
             ss += dv * dv;
@@ -137,7 +137,7 @@ __global__ void download_kernel(const BankT* __restrict__ data, int64_t row0, in
     if (i >= nrows * D) return;
     int64_t r = i / D;
     int d = static_cast<int>(i - r * D);
-    BankT v = data[static_cast<size_t>(row0 + r) * Dp + d];
+    BankT v = data[tile_offset(row0 + r, d, Dp / kKBlock)];
     if constexpr (sizeof(BankT) == 2) dst[i] = __bfloat162float(v);
     else dst[i] = v;
 }
@@ -164,10 +164,10 @@ int launch_ingest(const void* src, int src_dtype, int64_t n_items, int src_token
     return SKY_OK;
 }
 
-int launch_col_stats(const float* x, int64_t n_rows, int D, int ld, const float* mu_in, const float* sp_in,
-                     float* mean_out, float* std_out, cudaStream_t st) {
+int launch_col_stats(const float* x, int64_t n_rows, int D, int ld, int tiled_kblocks, const float* mu_in,
+                     const float* sp_in, float* mean_out, float* std_out, cudaStream_t st) {
     dim3 block(32, 8);
-    col_stats_kernel<<<(D + 31) / 32, block, 0, st>>>(x, n_rows, D, ld, mu_in, sp_in, mean_out, std_out);
+    col_stats_kernel<<<(D + 31) / 32, block, 0, st>>>(x, n_rows, D, ld, tiled_kblocks, mu_in, sp_in, mean_out, std_out);
     SKY_LAUNCH_CHECK("col_stats_kernel");
     return SKY_OK;
 }

@@ -47,8 +47,8 @@ void prof_mark(const sky_bank* b, cudaStream_t st);   // call right before and r
 int launch_ingest(const void* src, int src_dtype, int64_t n_items, int src_tokens, int token_mode,
                   int num_extra, int L, int D, int Dp, const float* mu, const float* sp, void* dst,
                   int dst_dtype, float* rownorm, int64_t dst_row0, cudaStream_t st);
-int launch_col_stats(const float* x, int64_t n_rows, int D, int ld, const float* mu_in, const float* sp_in,
-                     float* mean_out, float* std_out, cudaStream_t st);
+int launch_col_stats(const float* x, int64_t n_rows, int D, int ld, int tiled_kblocks, const float* mu_in,
+                     const float* sp_in, float* mean_out, float* std_out, cudaStream_t st);
 int launch_add_eps(const float* sigma, float* sp, int D, cudaStream_t st);
 int launch_finish_weights(const float* std_in, int D, int use_weights, float* w_out, cudaStream_t st);
 int launch_download(const void* data, int dtype, int64_t row0, int64_t nrows, int D, int Dp, float* dst,
@@ -71,6 +71,7 @@ struct SearchState {
 // simt_search.cu
 struct SimtArgs {
     const void* bank; int dtype;
+    int64_t row0;
     int64_t n_items; int L; int D; int Dp;
     const float* t; const float* w; int Q;
     int metric, combine, n_top;
@@ -88,6 +89,7 @@ int tc_grid(const sky_bank* b);
 int tc_make_bank_tmap(sky_bank* b);
 int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const SearchState& s, cudaStream_t st);
 size_t tc_scratch_bytes(const sky_bank* b, int Q);
+int debug_read_trace(unsigned long long* h_out, int n);
 
 // merge.cu
 int launch_init_state(const SearchState& s, int p_active, cudaStream_t st);

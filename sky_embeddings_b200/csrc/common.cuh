@@ -62,6 +62,21 @@ __host__ __device__ __forceinline__ bool metric_largest(int metric) { return met
 __host__ __device__ __forceinline__ int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // ---------------------------------------------------------------------------------------------
+// Bank layout in HBM: TILE-MAJOR.  Rows are grouped into tiles of 128, columns into k-blocks of
+// 64 elements; each (tile, k-block) is one contiguous [128 rows][64 elements] block, so that a
+// TMA box of the tensor path is a single contiguous 16 KB (bf16) read instead of 128 scattered
+// 128-byte bursts:
+//     element (row, d)  ->  ((row / 128) * KB + d / 64) * 8192 + (row % 128) * 64 + d % 64
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ size_t tile_row_base(int64_t row, int kblocks) {
+    return static_cast<size_t>(row >> 7) * kblocks * 8192 + static_cast<size_t>(row & 127) * 64;
+}
+__host__ __device__ __forceinline__ size_t tile_col_off(int d) { return static_cast<size_t>(d >> 6) * 8192 + (d & 63); }
+__host__ __device__ __forceinline__ size_t tile_offset(int64_t row, int d, int kblocks) {
+    return tile_row_base(row, kblocks) + tile_col_off(d);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side error plumbing (api.cu owns the storage)
 // ---------------------------------------------------------------------------------------------
 int set_error(int code, const char* fmt, ...);

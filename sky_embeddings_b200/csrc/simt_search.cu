@@ -19,6 +19,7 @@ constexpr int kRowsPerIter = 4;
 
 struct SimtParams {
     const void* bank;
+    int64_t row0;       // first bank row of item 0 (sky_score works on a sub-range)
     int64_t n_items;
     int L, D, Dp;
     const float* t;
@@ -134,12 +135,12 @@ __global__ void __launch_bounds__(kSimtThreads) simt_search_kernel(const SimtPar
             float s[kRowsPerIter][QC];
             for (int it = 0; it < n_tok_iters; ++it) {
                 const int64_t row0 = flat ? item_first : item_first * L + static_cast<int64_t>(it) * kRowsPerIter;
-                const BankT* rp[kRowsPerIter];
+                const BankT* rp[kRowsPerIter];     // tile-major: row base, then + tile_col_off(d)
 #pragma unroll
                 for (int r = 0; r < kRowsPerIter; ++r) {
                     int64_t row = row0 + r;
                     if (row >= total_rows) row = total_rows - 1;   // clamp; result masked below
-                    rp[r] = bank + static_cast<size_t>(row) * Dp;
+                    rp[r] = bank + tile_row_base(p.row0 + row, Dp / kKBlock);
                 }
                 float acc[kRowsPerIter][QC][NC];
 #pragma unroll
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kSimtThreads) simt_search_kernel(const SimtPar
                 for (int d0 = lane * 8; d0 < Dp; d0 += 256) {
                     float x[kRowsPerIter][8];
 #pragma unroll
-                    for (int r = 0; r < kRowsPerIter; ++r) load8<BankT>(rp[r] + d0, x[r]);
+                    for (int r = 0; r < kRowsPerIter; ++r) load8<BankT>(rp[r] + tile_col_off(d0), x[r]);
 #pragma unroll
                     for (int q = 0; q < QC; ++q) {
                         float a[8], wv[8];
@@ -390,7 +391,7 @@ int launch_simt_search(const sky_bank* b, const SimtArgs& a, const SearchState& 
                        cudaStream_t st) {
     for (int q0 = 0; q0 < a.Q; q0 += qc) {
         SimtParams p;
-        p.bank = a.bank; p.n_items = a.n_items; p.L = a.L; p.D = a.D; p.Dp = a.Dp;
+        p.bank = a.bank; p.row0 = a.row0; p.n_items = a.n_items; p.L = a.L; p.D = a.D; p.Dp = a.Dp;
         p.t = a.t; p.w = a.w; p.q0 = q0; p.nq = (a.Q - q0 < qc) ? (a.Q - q0) : qc;
         p.metric = a.metric; p.combine = a.combine; p.n_top = a.n_top;
         p.lists = s.lists; p.counts = s.counts; p.gtop = s.gtop; p.p_stride = s.p_stride; p.Qtot = s.Qtot;

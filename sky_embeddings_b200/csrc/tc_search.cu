@@ -12,32 +12,56 @@
 //   warps 2-5   epilogue: tcgen05.ld accumulators -> score -> threshold filter -> candidate sink
 //   warp 6      grid-wide threshold exchange (publishes / refreshes the top-k lower bound)
 // The bank streams from HBM exactly once per launch; no score ever goes to HBM.
+#include <cstdlib>
+
 #include "bank.cuh"
 #include "ptx.cuh"
 #include "topk.cuh"
 
 namespace sky {
 
-constexpr int kTcThreads = 7 * 32;
-constexpr int kEpiWarp0 = 2;
+constexpr int kProducerWarps = 4;               // warps 0-3: cp.async bank stream (warp 0 also loads B by TMA)
+constexpr int kEpiWarp0 = 4;                    // warps 4-7: epilogue (warp & 3 = TMEM lane quarter)
+constexpr int kMmaWarp = 8;                     // warp 8: MMA issuer, owns TMEM
+constexpr int kXchgWarp = 9;                    // warp 9: grid-wide threshold exchange
+constexpr int kTcThreads = 10 * 32;
+constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpiThreads = 128;
-constexpr int kStageBytes = kTileRows * 128;   // 128 rows x 64 bf16
+constexpr int kStageBytes = kTileRows * 128;   // 128 rows x 64 bf16 = one contiguous (tile, k-block) of the bank
 constexpr int kMaxStages = 8;
 
 struct TcParams {
+    const unsigned char* bank;   // tile-major bf16 bank
     const float* rownorm;   // [rows_pad]
     const float* qconst;    // [BN] cosine: |t| ; MSE: |t|^2
     uint64_t* lists; int* counts; uint32_t* gtop; uint32_t* gtau;
     int p_stride, Qtot, q0, nq, cap, k, use_gtau;
     int64_t rows;           // valid bank rows
     int num_tiles, kblocks, stages, metric;
+    unsigned long long bank_policy;   // L2 cache hint of the bank stream
+    int debug;              // bit0: epilogue skips scoring, bit1: MMA skipped, bit2: contiguous tiles (experiments)
     float inv_dd;           // 1 / D^2
 };
 
+// 16-byte async copy global -> shared with an L2 eviction hint (the bank is streamed once)
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "l"(policy)
+                 : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
+}
+
+// debug timeline (SKY_TC_DEBUG bit 3): clock64 stamps of CTA 0, rows: 0 producer issue, 1 MMA saw full,
+// 2 MMA committed, 3 epilogue saw tmem_full, 4 epilogue tile done
+constexpr int kTraceLen = 1024;
+__device__ unsigned long long g_trace[6 * kTraceLen];   // row 5: per-tile counters of CTA 0 (slow groups of warp e=0)
+#define SKY_TRACE(row, i) do { if ((p.debug & 8) && blockIdx.x == 0 && (i) < kTraceLen) g_trace[(row) * kTraceLen + (i)] = clock64(); } while (0)
+
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_constant__ CUtensorMap tmap_q,
-                 const TcParams p) {
+tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment is required by the 128-byte swizzle atoms
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -50,7 +74,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
     uint64_t* b_full = empty_bar + kMaxStages;                  // [1]
     uint64_t* tmem_full = b_full + 1;                           // [2]
     uint64_t* tmem_empty = tmem_full + 2;                       // [2]
-    unsigned long long* sThr = reinterpret_cast<unsigned long long*>(tmem_empty + 2);   // [BN]
+    // 16-byte aligned: the threshold / constant arrays are read with 128-bit shared loads
+    unsigned long long* sThr = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(tmem_empty + 2) + 15) & ~uintptr_t(15));   // [BN]
     float* sQc = reinterpret_cast<float*>(sThr + BN);           // [BN]
     float* sThrF = sQc + BN;                                    // [BN] threshold as a score (pre-filter)
     int* sCnt = reinterpret_cast<int*>(sThrF + BN);             // [BN]
@@ -63,26 +88,34 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
     const bool largest = (p.metric == SKY_COSINE);
 
     // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int my_tiles = (p.num_tiles > static_cast<int>(blockIdx.x))
-                             ? (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
-                             : 0;
+    const int tiles_per_cta = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    int my_tiles = (p.num_tiles > static_cast<int>(blockIdx.x))
+                       ? (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                       : 0;
+    if (p.debug & 4) {   // experiment: contiguous tile range per CTA
+        const int lo = static_cast<int>(blockIdx.x) * tiles_per_cta;
+        my_tiles = p.num_tiles > lo ? min(tiles_per_cta, p.num_tiles - lo) : 0;
+    }
+    auto tile_of = [&](int it) -> int {
+        return (p.debug & 4) ? static_cast<int>(blockIdx.x) * tiles_per_cta + it : static_cast<int>(blockIdx.x + it * gridDim.x);
+    };
 
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&tmap_bank);
         ptx::prefetch_tmap(&tmap_q);
-        for (int s = 0; s < S; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < S; ++s) { ptx::mbar_init(&full_bar[s], kProducerThreads); ptx::mbar_init(&empty_bar[s], 1); }
         ptx::mbar_init(b_full, 1);
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
         ptx::fence_barrier_init();
         *sTilesDone = 0;
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         ptx::tmem_alloc(sTmemBase, 2 * BN);
         ptx::tmem_relinquish();
     }
     for (int q = tid; q < BN; q += kTcThreads) {
         sThr[q] = (q < p.nq) ? 0ull : ~0ull;
-        sThrF[q] = __uint_as_float(0x7FC00000u);   // NaN: the pre-filter lets everything through
+        // NaN lets everything through the pre-filter; padding queries are rejected by it
+        sThrF[q] = (q < p.nq) ? __uint_as_float(0x7FC00000u) : (largest ? INFINITY : -INFINITY);
         sQc[q] = p.qconst[q];
         sCnt[q] = 0;
         sLmax[q] = 0;
@@ -97,26 +130,43 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
     sink.thr = smem_addr(sThr); sink.thr_f = smem_addr(sThrF); sink.cnt = smem_addr(sCnt); sink.lmax = smem_addr(sLmax);
     sink.cap = p.cap; sink.k = p.k; sink.largest = largest;
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+    if (warp < kProducerWarps) {
+        // ===================== bank stream: cp.async producers =====================
+        // Each (tile, k-block) is one contiguous 16 KB block in HBM (tile-major bank).  128 threads copy
+        // it as 1024 16-byte chunks into the 128-byte-swizzled layout the UMMA descriptors expect:
+        // chunk (row, c) -> row * 128 + ((c ^ (row & 7)) << 4).  The stage's full barrier gets one
+        // arrival per producer thread when that thread's copies have landed.
+        if (tid == 0) {
             ptx::mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(KB) * BN * 128);
             for (int kb = 0; kb < KB; ++kb)
                 ptx::tma_load_2d(&tmap_q, sB + static_cast<size_t>(kb) * BN * 128, b_full, kb * kKBlock, 0, ptx::kEvictLast);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                const int tile = blockIdx.x + it * gridDim.x;
-                for (int kb = 0; kb < KB; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-                    ptx::tma_load_2d(&tmap_bank, sA + static_cast<size_t>(stage) * kStageBytes, &full_bar[stage],
-                                     kb * kKBlock, tile * kTileRows, ptx::kEvictFirst);
-                    if (++stage == S) { stage = 0; phase ^= 1; }
-                }
+        }
+        uint32_t dst_off[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = j * kProducerThreads + tid;           // chunk index in the block
+            const int row = g >> 3, c = g & 7;
+            dst_off[j] = static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4));
+        }
+        const uint32_t sA_addr = ptx::smem_u32(sA);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const unsigned char* src = p.bank + (static_cast<size_t>(tile_of(it)) * KB) * kStageBytes + static_cast<size_t>(tid) * 16;
+            for (int kb = 0; kb < KB; ++kb) {
+                if (lane == 0) ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                __syncwarp();
+                if (tid == 0) SKY_TRACE(0, it * KB + kb);
+                const uint32_t dst = sA_addr + static_cast<uint32_t>(stage) * kStageBytes;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    cp_async_16(dst + dst_off[j], src + static_cast<size_t>(j) * kProducerThreads * 16, p.bank_policy);
+                cp_async_arrive_noinc(&full_bar[stage]);
+                src += kStageBytes;
+                if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileRows, BN);
@@ -132,6 +182,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
+                    SKY_TRACE(1, it * KB + kb);
+                    ptx::fence_proxy_async();                 // cp.async (generic proxy) writes -> UMMA (async proxy) reads
                     ptx::tc_fence_after();
                     const uint32_t a_addr = ptx::smem_u32(sA + static_cast<size_t>(stage) * kStageBytes);
                     const uint32_t b_addr = ptx::smem_u32(sB + static_cast<size_t>(kb) * BN * 128);
@@ -139,70 +191,108 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
                     for (int k = 0; k < kKBlock / 16; ++k) {
                         const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_addr + k * 32);
                         const uint64_t b_desc = ptx::make_sw128_kmajor_desc(b_addr + k * 32);
-                        ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(p.debug & 2)) ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty_bar[stage]);      // stage reusable once these MMAs retire
+                    SKY_TRACE(2, it * KB + kb);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(&tmem_full[acc]);            // accumulator ready for the epilogue
             }
         }
-    } else if (warp < kEpiWarp0 + 4) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
         // ===================== epilogue =====================
         const int e = warp - kEpiWarp0;
         const int quarter = warp & 3;                          // TMEM lanes this warp may access
         const uint32_t hist = smem_addr(sHist + e * 256);
+        const uint32_t thrf_addr = smem_addr(sThrF);
+        const uint32_t qc_addr = smem_addr(sQc);
+        // row norms are prefetched two tiles ahead: a cold load under a saturated HBM stream costs
+        // thousands of cycles, which would otherwise be exposed once per tile
+        auto load_rn = [&](int it) -> float {
+            if (it >= my_tiles) return 0.f;
+            const int64_t r = static_cast<int64_t>(tile_of(it)) * kTileRows + quarter * 32 + lane;
+            return r < p.rows ? __ldg(p.rownorm + r) : 0.f;
+        };
+        float rn_cur = load_rn(0), rn_nxt = load_rn(1);
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
+            const int tile = tile_of(it);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int64_t row = static_cast<int64_t>(tile) * kTileRows + quarter * 32 + lane;
             const bool valid = row < p.rows;
-            const float rn = valid ? __ldg(p.rownorm + row) : 0.f;
-            ptx::mbar_wait(&tmem_full[acc], acc_phase);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
-            uint32_t v[BN];
-#pragma unroll
-            for (int c = 0; c < BN / 32; ++c) ptx::tmem_ld_32x32b_x32(taddr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);   // accumulator stage free again
-
+            const float rn = rn_cur;
+            rn_cur = rn_nxt;
+            rn_nxt = load_rn(it + 2);
             const float mx = sqrtf(rn);
             const uint32_t ridx = static_cast<uint32_t>(row);
+            if (lane == 0) ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            __syncwarp();
+            if (e == 0 && lane == 0) SKY_TRACE(3, it);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll
-            for (int q = 0; q < BN; ++q) {
-                if (q < p.nq) {                                  // warp-uniform
-                    const float dot = __uint_as_float(v[q]);
-                    const float thf = sink_thr_score(sink, q);
-                    // cheap, conservative pre-filter in the space of the accumulator: no division,
-                    // no key; NaN always goes on to the exact test (NaN ranks first for cosine)
-                    float den = 0.f, s = 0.f;
-                    bool maybe;
-                    if (largest) {
-                        den = fmaf(sQc[q], mx, 1e-6f);
-                        float bound = thf * den;
-                        bound = fmaf(-fabsf(bound), 1e-6f, bound);
-                        maybe = !(dot < bound);
-                    } else {
-                        s = (sQc[q] - 2.0f * dot + rn) * p.inv_dd;
-                        maybe = !(s > thf);
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+                ptx::tmem_ld_wait();
+                if (c == BN / 32 - 1) {                        // last chunk is in registers: free the accumulator
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+                }
+                if (p.debug & 1) continue;
+                // FAST PATH, branch-free and compact (instruction-cache friendly): 32 conservative
+                // pre-filters in the space of the accumulator -- no division, no key -- into one bitmask.
+                // Thresholds are read with vector loads and may be slightly stale (they only tighten);
+                // padding queries carry a rejecting threshold; NaN always goes on to the exact test
+                // (NaN ranks first for cosine).
+                uint32_t mbits = 0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const int q0 = c * 32 + g * 4;
+                    float th[4], qc[4];
+                    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(th[0]), "=f"(th[1]), "=f"(th[2]), "=f"(th[3]) : "r"(thrf_addr + q0 * 4) : "memory");
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(qc[0]), "=f"(qc[1]), "=f"(qc[2]), "=f"(qc[3]) : "r"(qc_addr + q0 * 4));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float dot = __uint_as_float(v[g * 4 + u]);
+                        bool m;
+                        if (largest) {
+                            float bound = th[u] * fmaf(qc[u], mx, 1e-6f);
+                            bound = fmaf(-fabsf(bound), 1e-6f, bound);
+                            m = !(dot < bound);
+                        } else {
+                            m = !((qc[u] - 2.0f * dot + rn) * p.inv_dd > th[u]);
+                        }
+                        mbits |= (m ? 1u : 0u) << (g * 4 + u);
                     }
-                    maybe = maybe && valid;
-                    if (__any_sync(0xffffffffu, maybe)) {
-                        if (largest) s = dot / den;
-                        const uint64_t comp = make_composite(score_to_key(s, largest), ridx);
-                        const bool pass = maybe && (comp > sink_thr(sink, q));
-                        sink_insert_rows(sink, q, pass, comp);
-                    }
+                }
+                mbits = valid ? mbits : 0u;
+                // EXACT PATH, rare after warm-up: a compact loop over the queries with a survivor in this warp
+                uint32_t todo = __reduce_or_sync(0xffffffffu, mbits);
+#pragma unroll 1
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int q = c * 32 + j;
+                    if (q >= p.nq) continue;
+                    float dot = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) dot = (jj == j) ? __uint_as_float(v[jj]) : dot;
+                    const float qcv = sQc[q];
+                    const float sv = largest ? dot / fmaf(qcv, mx, 1e-6f) : (qcv - 2.0f * dot + rn) * p.inv_dd;
+                    const uint64_t comp = make_composite(score_to_key(sv, largest), ridx);
+                    const bool pass = ((mbits >> j) & 1u) && (comp > sink_thr(sink, q));
+                    sink_insert_rows(sink, q, pass, comp);
                 }
             }
             ptx::named_bar_sync(1, kEpiThreads);
             sink_prune_if_full(sink, p.nq, e, 4, hist);
             ptx::named_bar_sync(1, kEpiThreads);
-            if (e == 0 && lane == 0) *sTilesDone = it + 1;
+            if (e == 0 && lane == 0) { *sTilesDone = it + 1; SKY_TRACE(4, it); }
         }
         // final: counts and the last published bound
         ptx::named_bar_sync(1, kEpiThreads);
@@ -211,7 +301,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
             const uint32_t mine = lds_u32(sink.lmax + q * 4);
             if (p.use_gtau && mine) st_cg_u32(p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q, mine);
         }
-    } else {
+    } else if (warp == kXchgWarp) {
         // ===================== threshold exchange =====================
         // publish this CTA's best keys, reduce one query column for everybody, apply all bounds;
         // runs free of the epilogue (all state is monotone), fast at first, then at a trickle
@@ -232,10 +322,17 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_con
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, 2 * BN);
     }
+}
+
+int debug_read_trace(unsigned long long* h_out, int n) {
+    if (n > 6 * kTraceLen) n = 6 * kTraceLen;
+    SKY_CUDA(cudaDeviceSynchronize());
+    SKY_CUDA(cudaMemcpyFromSymbol(h_out, g_trace, sizeof(unsigned long long) * n));
+    return SKY_OK;
 }
 
 // Queries -> bf16 operand matrix [q_pad, Dp] (zero padded) + per-query constants.
@@ -281,7 +378,7 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, Dp] tensor, box = 64 columns x box_rows rows, 128-byte swizzle.
+// 2-D bf16 [rows, Dp] tensor (row pitch Dp elements), box = 64 columns x box_rows rows, 128-byte swizzle.
 static int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_error(SKY_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -299,7 +396,7 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, i
 constexpr int kTcBN = 64;
 
 static size_t tc_tail_bytes(int BN) {
-    return (2 * kMaxStages + 1 + 4) * sizeof(uint64_t) + BN * (8 + 4 + 4 + 4 + 4) + 4 * 256 * 4 + 16;
+    return (2 * kMaxStages + 1 + 4) * sizeof(uint64_t) + 16 + BN * (8 + 4 + 4 + 4 + 4) + 4 * 256 * 4 + 16;
 }
 
 static int tc_stages(int Dp, int BN) {
@@ -322,7 +419,8 @@ int tc_grid(const sky_bank* b) {
 }
 
 int tc_make_bank_tmap(sky_bank* b) {
-    int rc = make_tmap_2d(&b->tmap_bank, b->data, b->rows_pad, b->Dp, kTileRows);
+    // tile-major bank: a [rows_pad * KB, 64] tensor whose 128-row boxes are the contiguous (tile, k-block) blocks
+    int rc = make_tmap_2d(&b->tmap_bank, b->data, b->rows_pad * (b->Dp / kKBlock), kKBlock, kTileRows);
     if (rc) return rc;
     b->tmap_ready = true;
     return SKY_OK;
@@ -335,7 +433,6 @@ size_t tc_scratch_bytes(const sky_bank* b, int Q) {
 
 // scratch (bank->ws2): [q_pad, Dp] bf16 | [q_pad] f32
 int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const SearchState& s, cudaStream_t st) {
-    if (!b->tmap_ready) return set_error(SKY_ERR_STATE, "bank has no TMA descriptor (finalize first)");
     constexpr int BN = kTcBN;
     const int q_pad = static_cast<int>(round_up(Q, BN));
     __nv_bfloat16* bq = reinterpret_cast<__nv_bfloat16*>(b->ws2);
@@ -344,15 +441,18 @@ int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const Searc
     pack_queries_kernel<<<q_pad, 256, 0, st>>>(t, Q, b->D, b->Dp, q_pad, metric, bq, qconst);
     SKY_LAUNCH_CHECK("pack_queries_kernel");
 
-    const int stages = tc_stages(b->Dp, BN);
+    int stages = tc_stages(b->Dp, BN);
+    { static const char* e = getenv("SKY_TC_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
     const size_t smem = 1024 + static_cast<size_t>(b->Dp) * BN * 2 + static_cast<size_t>(stages) * kStageBytes + tc_tail_bytes(BN);
     SKY_CUDA(cudaFuncSetAttribute(tc_search_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const int grid = s.P;
+    int grid = s.P;
+    { static const char* e = getenv("SKY_TC_GRID"); if (e && atoi(e) >= 1 && atoi(e) < grid) grid = atoi(e); }
     for (int q0 = 0; q0 < Q; q0 += BN) {
         CUtensorMap tmq;
         int rc = make_tmap_2d(&tmq, bq + static_cast<size_t>(q0) * b->Dp, BN, b->Dp, BN);
         if (rc) return rc;
         TcParams p;
+        p.bank = reinterpret_cast<const unsigned char*>(b->data);
         p.rownorm = b->rownorm;
         p.qconst = qconst + q0;
         p.lists = s.lists; p.counts = s.counts; p.gtop = s.gtop; p.gtau = s.gtau;
@@ -363,9 +463,12 @@ int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const Searc
         p.kblocks = b->Dp / kKBlock;
         p.stages = stages;
         p.metric = metric;
+        { static const char* dbg = getenv("SKY_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+        { static const char* pol = getenv("SKY_TC_POLICY"); const int pv = pol ? atoi(pol) : 0;
+          p.bank_policy = pv == 1 ? 0x1000000000000000ull /* evict normal */ : (pv == 2 ? ptx::kEvictLast : ptx::kEvictFirst); }
         p.inv_dd = 1.0f / (static_cast<float>(b->D) * static_cast<float>(b->D));
         prof_mark(b, st);
-        tc_search_kernel<BN><<<grid, kTcThreads, smem, st>>>(b->tmap_bank, tmq, p);
+        tc_search_kernel<BN><<<grid, kTcThreads, smem, st>>>(tmq, p);
         prof_mark(b, st);
         SKY_LAUNCH_CHECK("tc_search_kernel");
     }
