@@ -261,6 +261,8 @@ int sky_bank_finalize(sky_bank_t* b, void* stream) {
 /* debug only (not part of the public header): timeline of the tensor kernel, see tc_search.cu */
 __attribute__((visibility("default"))) int sky_debug_trace(unsigned long long* h_out, int n) { return debug_read_trace(h_out, n); }
 
+__attribute__((visibility("default"))) int sky_debug_epi(unsigned long long* h_out) { return debug_read_epi(h_out); }
+
 int sky_profile_enable(sky_bank_t* b, int enable) {
     if (!b) return set_error(SKY_ERR_ARG, "bank is NULL");
     if (!b->prof_events) b->prof_events = new std::vector<cudaEvent_t>();

@@ -90,6 +90,7 @@ int tc_make_bank_tmap(sky_bank* b);
 int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const SearchState& s, cudaStream_t st);
 size_t tc_scratch_bytes(const sky_bank* b, int Q);
 int debug_read_trace(unsigned long long* h_out, int n);
+int debug_read_epi(unsigned long long* h_out);
 
 // merge.cu
 int launch_init_state(const SearchState& s, int p_active, cudaStream_t st);

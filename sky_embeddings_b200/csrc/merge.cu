@@ -17,7 +17,7 @@ constexpr int kMaxK = 4096;
 
 __global__ void init_state_kernel(uint32_t* gtop, uint32_t* gtau, int* counts, int Qtot, int p_stride, int p_active, int P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < Qtot * p_stride) gtop[i] = ((i / Qtot) < p_active) ? 0u : 0xFFFFFFFFu;   // [p][q]
+    if (i < Qtot * p_stride) gtop[i] = 0u;   // [p][q]; 0 = nothing published
     if (i < Qtot * P) counts[i] = 0;
     if (i < Qtot) gtau[i] = 0u;
 }
@@ -47,17 +47,16 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nwarps = kMergeThreads / 32;
 
-    if (tid == 0) { npool = 0; tau_s = 0xFFFFFFFFu; }
+    if (tid == 0) { npool = 0; tau_s = 0u; }
     __syncthreads();
-    if (use_gtau) {
-        uint32_t lo = 0xFFFFFFFFu;
-        for (int p = tid; p < p_stride; p += kMergeThreads) lo = min(lo, gtop[static_cast<size_t>(p) * Qtot + q]);
-        lo = __reduce_min_sync(0xffffffffu, lo);
-        if (lane == 0) atomicMin(&tau_s, lo);
+    // final grid-wide bound: the k-th largest of the per-CTA best keys (see topk.cuh)
+    if (use_gtau && warp == 0) {
+        const uint32_t lo = exchange_reduce(gtop + q, p_stride, Qtot, k);
+        if (lane == 0) tau_s = lo;
     }
     __syncthreads();
     // every composite with key >= tau must be kept; tau == 0 / disabled keeps everything valid
-    const uint64_t keep_ge = (use_gtau && tau_s != 0u && tau_s != 0xFFFFFFFFu) ? (static_cast<uint64_t>(tau_s) << 32) : 1ull;
+    const uint64_t keep_ge = (use_gtau && tau_s != 0u) ? (static_cast<uint64_t>(tau_s) << 32) : 1ull;
 
     for (int p = warp; p < P; p += nwarps) {
         const int n = counts[static_cast<size_t>(p) * Qtot + q];

@@ -41,6 +41,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Latency-tolerant wait: the suspend-time hint lets the hardware park the thread until the phase
+// completes instead of re-polling, and the back-off keeps spinning waiters from flooding the shared
+// memory pipe (every poll is a shared-memory transaction that delays the epilogue's LDS/ATOMS).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 64) {
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) break;
+        __nanosleep(sleep_ns);
+    }
+}
 
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {

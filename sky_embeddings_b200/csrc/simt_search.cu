@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kSimtThreads) simt_search_kernel(const SimtPar
                 // gtop is [cta][query]: publish this CTA's row, then min over CTAs per query column
                 if (warp == kSimtWarps - 1) exchange_publish(sink, p.nq, p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0);
                 for (int q = warp; q < p.nq; q += kSimtWarps) {
-                    const uint32_t lo = exchange_reduce(p.gtop + p.q0 + q, p.p_stride, p.Qtot);
+                    const uint32_t lo = exchange_reduce(p.gtop + p.q0 + q, p.p_stride, p.Qtot, p.k);
                     if (lane == 0) exchange_apply(sink, q, lo);
                 }
             }

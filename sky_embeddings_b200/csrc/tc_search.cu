@@ -57,6 +57,8 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 // 2 MMA committed, 3 epilogue saw tmem_full, 4 epilogue tile done
 constexpr int kTraceLen = 1024;
 __device__ unsigned long long g_trace[6 * kTraceLen];   // row 5: per-tile counters of CTA 0 (slow groups of warp e=0)
+__device__ unsigned long long g_epi[64 * 12];   // per-tile stamps inside the epilogue of CTA 0, warp e=0
+#define SKY_EPI(it, slot) do { if ((p.debug & 8) && blockIdx.x == 0 && e == 0 && lane == 0 && (it) < 64) g_epi[(it) * 12 + (slot)] = clock64(); } while (0)
 #define SKY_TRACE(row, i) do { if ((p.debug & 8) && blockIdx.x == 0 && (i) < kTraceLen) g_trace[(row) * kTraceLen + (i)] = clock64(); } while (0)
 
 template <int BN>
@@ -154,7 +156,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
         for (int it = 0; it < my_tiles; ++it) {
             const unsigned char* src = p.bank + (static_cast<size_t>(tile_of(it)) * KB) * kStageBytes + static_cast<size_t>(tid) * 16;
             for (int kb = 0; kb < KB; ++kb) {
-                if (lane == 0) ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (lane == 0) ptx::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                 __syncwarp();
                 if (tid == 0) SKY_TRACE(0, it * KB + kb);
                 const uint32_t dst = sA_addr + static_cast<uint32_t>(stage) * kStageBytes;
@@ -177,11 +179,11 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
             for (int it = 0; it < my_tiles; ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                ptx::mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1, 32);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
                 for (int kb = 0; kb < KB; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);
                     SKY_TRACE(1, it * KB + kb);
                     ptx::fence_proxy_async();                 // cp.async (generic proxy) writes -> UMMA (async proxy) reads
                     ptx::tc_fence_after();
@@ -226,7 +228,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
             rn_nxt = load_rn(it + 2);
             const float mx = sqrtf(rn);
             const uint32_t ridx = static_cast<uint32_t>(row);
-            if (lane == 0) ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            if (lane == 0) ptx::mbar_wait_relaxed(&tmem_full[acc], acc_phase, 128);
             __syncwarp();
             if (e == 0 && lane == 0) SKY_TRACE(3, it);
             ptx::tc_fence_after();
@@ -234,8 +236,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
+                SKY_EPI(it, c * 4 + 0);
                 ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
                 ptx::tmem_ld_wait();
+                SKY_EPI(it, c * 4 + 1);
                 if (c == BN / 32 - 1) {                        // last chunk is in registers: free the accumulator
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -271,27 +275,30 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
                     }
                 }
                 mbits = valid ? mbits : 0u;
-                // EXACT PATH, rare after warm-up: a compact loop over the queries with a survivor in this warp
-                uint32_t todo = __reduce_or_sync(0xffffffffu, mbits);
+                SKY_EPI(it, c * 4 + 2);
+                // EXACT PATH, rare after warm-up: every lane walks its own survivors (the warp runs as many
+                // rounds as the busiest lane has bits); inserts are per-lane shared-memory atomics
 #pragma unroll 1
-                while (todo) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1;
+                while (mbits) {
+                    const int j = __ffs(mbits) - 1;
+                    mbits &= mbits - 1;
                     const int q = c * 32 + j;
                     if (q >= p.nq) continue;
                     float dot = 0.f;
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) dot = (jj == j) ? __uint_as_float(v[jj]) : dot;
-                    const float qcv = sQc[q];
+                    const float qcv = lds_f32(qc_addr + q * 4);
                     const float sv = largest ? dot / fmaf(qcv, mx, 1e-6f) : (qcv - 2.0f * dot + rn) * p.inv_dd;
-                    const uint64_t comp = make_composite(score_to_key(sv, largest), ridx);
-                    const bool pass = ((mbits >> j) & 1u) && (comp > sink_thr(sink, q));
-                    sink_insert_rows(sink, q, pass, comp);
+                    sink_insert_one(sink, q, make_composite(score_to_key(sv, largest), ridx));
                 }
+                SKY_EPI(it, c * 4 + 3);
             }
             ptx::named_bar_sync(1, kEpiThreads);
+            SKY_EPI(it, 8);
             sink_prune_if_full(sink, p.nq, e, 4, hist);
+            SKY_EPI(it, 9);
             ptx::named_bar_sync(1, kEpiThreads);
+            SKY_EPI(it, 10);
             if (e == 0 && lane == 0) { *sTilesDone = it + 1; SKY_TRACE(4, it); }
         }
         // final: counts and the last published bound
@@ -311,7 +318,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
             int round = 0;
             while (*sTilesDone < my_tiles) {
                 exchange_publish(sink, p.nq, my_row);
-                const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot);
+                const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot, p.k);
                 if (lane == 0 && lo != 0u) atomicMax(p.gtau + p.q0 + rq, lo);
                 for (int q = lane; q < p.nq; q += 32) exchange_apply(sink, q, ld_cg_u32(p.gtau + p.q0 + q));
                 ++round;
@@ -332,6 +339,11 @@ int debug_read_trace(unsigned long long* h_out, int n) {
     if (n > 6 * kTraceLen) n = 6 * kTraceLen;
     SKY_CUDA(cudaDeviceSynchronize());
     SKY_CUDA(cudaMemcpyFromSymbol(h_out, g_trace, sizeof(unsigned long long) * n));
+    return SKY_OK;
+}
+int debug_read_epi(unsigned long long* h_out) {
+    SKY_CUDA(cudaDeviceSynchronize());
+    SKY_CUDA(cudaMemcpyFromSymbol(h_out, g_epi, sizeof(g_epi)));
     return SKY_OK;
 }
 

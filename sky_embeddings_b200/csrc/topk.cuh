@@ -195,17 +195,28 @@ __device__ __forceinline__ void sink_prune(const Sink& s, int q, uint32_t hist) 
 // Called by `nwarps` warps (warp_in_group = 0..nwarps-1) between two barriers.
 __device__ __forceinline__ void sink_prune_if_full(const Sink& s, int nq, int warp_in_group, int nwarps,
                                                    uint32_t hist) {
-    for (int q = warp_in_group; q < nq; q += nwarps)
-        if (static_cast<int>(lds_u32(s.cnt + q * 4)) > s.cap - kPruneSlack) sink_prune(s, q, hist);
+    // one vector pass over the counts instead of a serial chain of dependent shared loads
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < nq; base += 32 * nwarps) {
+        const int q = base + lane * nwarps + warp_in_group;      // this warp owns q % nwarps == warp_in_group
+        const bool full = q < nq && static_cast<int>(lds_u32(s.cnt + q * 4)) > s.cap - kPruneSlack;
+        uint32_t todo = __ballot_sync(0xffffffffu, full);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            sink_prune(s, base + l * nwarps + warp_in_group, hist);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Grid-wide bound exchange.
-//   gtop [p_stride][Qtot] u32: row p = best key CTA p has inserted per query (0 = nothing yet; rows
-//                              of CTAs without work hold 0xFFFFFFFF)
-//   gtau [Qtot] u32:           min over p of gtop[p][q], maintained by designated reducer CTAs
-// If k <= #CTAs with work, at least k bank rows have key >= gtau[q], so a candidate with a smaller
-// key can never be in the global top-k.  All values only grow; every race is benign.
+//   gtop [p_stride][Qtot] u32: row p = best key CTA p has inserted per query (0 = nothing yet)
+//   gtau [Qtot] u32:           the k-th largest entry of column q, maintained by reducer CTAs
+// Every published key belongs to a DIFFERENT bank row (CTAs own disjoint rows) that sits in its
+// CTA's candidate list, so at least k rows have key >= (k-th largest published key): a candidate
+// with a smaller key can never be in the global top-k.  Fewer than k published keys give 0 = no
+// information.  All values only grow; every race is benign.
 // ---------------------------------------------------------------------------------------------
 // publish this CTA's best keys for queries [0, nq) (one warp)
 __device__ __forceinline__ void exchange_publish(const Sink& s, int nq, uint32_t* gtop_row) {
@@ -214,12 +225,38 @@ __device__ __forceinline__ void exchange_publish(const Sink& s, int nq, uint32_t
         if (mine) st_cg_u32(gtop_row + q, mine);
     }
 }
-// one warp: min over CTAs of query column q  ->  gtau
-__device__ __forceinline__ uint32_t exchange_reduce(const uint32_t* gtop_col, int p_stride, int q_stride) {
+// one warp: k-th largest (1-based) of one query column of gtop; p_stride <= 32 * kMaxPerLane
+constexpr int kXchgPerLane = 32;   // up to 1024 CTAs
+__device__ __forceinline__ uint32_t exchange_reduce(const uint32_t* gtop_col, int p_stride, int q_stride, int k) {
     const int lane = threadIdx.x & 31;
-    uint32_t lo = 0xFFFFFFFFu;
-    for (int p = lane; p < p_stride; p += 32) lo = min(lo, ld_cg_u32(gtop_col + static_cast<size_t>(p) * q_stride));
-    return __reduce_min_sync(0xffffffffu, lo);
+    // bitwise binary search for the largest x with #{v >= x} >= k, values re-read from L2 each round
+    // would be slow: keep them in registers (fixed upper bound, predicated)
+    uint32_t v[8];
+    uint32_t prefix = 0;
+    if (p_stride <= 256) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int p = lane + 32 * i;
+            v[i] = p < p_stride ? ld_cg_u32(gtop_col + static_cast<size_t>(p) * q_stride) : 0u;
+        }
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = prefix | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c += (v[i] >= cand);
+            if (__reduce_add_sync(0xffffffffu, c) >= k) prefix = cand;
+        }
+    } else {
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = prefix | (1u << bit);
+            int c = 0;
+            for (int p = lane; p < p_stride; p += 32) c += (ld_cg_u32(gtop_col + static_cast<size_t>(p) * q_stride) >= cand);
+            if (__reduce_add_sync(0xffffffffu, c) >= k) prefix = cand;
+        }
+    }
+    return prefix;
 }
 // raise the local threshold of query q to the grid-wide bound `lo` (a key; 0 = no information)
 __device__ __forceinline__ void exchange_apply(const Sink& s, int q, uint32_t lo) {

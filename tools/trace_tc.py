@@ -28,7 +28,15 @@ print("k-block events (cycles since first producer issue), first", nk)
 for i in range(nk):
     print(i, *(int(a[r, i] - t0) for r in range(3)))
 print("tile events")
-for i in range(53):
+for i in range(22):
     print(i, int(a[3, i] - t0), int(a[4, i] - t0), 'epilogue cycles', int(a[4, i] - a[3, i]), 'slow groups (of 16, x3 searches)', int(a[5, i]))
+eb = (C.c_ulonglong * (64 * 12))()
+lib.sky_debug_epi.argtypes = [C.c_void_p]
+lib.sky_debug_epi(eb)
+ep = np.array(eb[:], dtype=np.int64).reshape(64, 12)
+print("epilogue breakdown per tile (cycles): ld0 fast0 slow0 | ld1 fast1 slow1 | bar1 prune bar2")
+for i in range(22):
+    r = ep[i]
+    print(i, r[1]-r[0], r[2]-r[1], r[3]-r[2], '|', r[5]-r[4], r[6]-r[5], r[7]-r[6], '|', r[8]-r[7], r[9]-r[8], r[10]-r[9])
 d = np.diff(a[1, :200])
 print("mean cycles between full-barrier completions (k-blocks 12..200):", d[12:].mean())
