@@ -85,6 +85,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
     uint32_t* sHist = sLmax + BN;                               // [4][256]
     uint32_t* sTmemBase = sHist + 4 * 256;                      // [1]
     volatile int* sTilesDone = reinterpret_cast<volatile int*>(sTmemBase + 1);   // [1]
+    volatile int* sBoot = sTilesDone + 1;   // [1] 0 = not started, 1 = tile-0 maxima ready, 2 = bounds applied
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool largest = (p.metric == SKY_COSINE);
@@ -109,6 +110,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
         ptx::fence_barrier_init();
         *sTilesDone = 0;
+        *sBoot = 0;
     }
     if (warp == kMmaWarp) {
         ptx::tmem_alloc(sTmemBase, 2 * BN);
@@ -233,6 +235,35 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
             if (e == 0 && lane == 0) SKY_TRACE(3, it);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            if (it == 0 && p.use_gtau && !(p.debug & 1)) {
+                // BOOTSTRAP (once per launch): with no bound yet, every row of the first tile would be a
+                // candidate for every query.  Instead read the accumulator twice: this first pass only takes
+                // the per-query maximum of the tile, the exchange warp trades maxima with the other CTAs,
+                // and the normal pass below then runs with a grid-wide bound already in place.
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int q = c * 32 + j;
+                        const float dot = __uint_as_float(v[j]);
+                        const float qcv = sQc[q];
+                        const float sv = largest ? dot / fmaf(qcv, mx, 1e-6f) : (qcv - 2.0f * dot + rn) * p.inv_dd;
+                        const uint32_t key = (valid && q < p.nq) ? score_to_key(sv, largest) : 0u;
+                        const uint32_t best = __reduce_max_sync(0xffffffffu, key);
+                        if (lane == 0 && best) reds_max_u32(sink.lmax + q * 4, best);
+                    }
+                }
+                ptx::named_bar_sync(1, kEpiThreads);
+                if (e == 0 && lane == 0) *sBoot = 1;
+                if (lane == 0) {
+                    const long long t_end = clock64() + 60000;         // ~30 us: never wait for a bound forever
+                    while (*sBoot != 2 && clock64() < t_end) __nanosleep(100);
+                }
+                __syncwarp();
+            }
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
@@ -316,6 +347,26 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
             uint32_t* my_row = p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0;
             const int rq = static_cast<int>(blockIdx.x) % p.nq;
             int round = 0;
+            // bootstrap: wait for the tile-0 maxima, then trade them until every query has a bound
+            while (*sBoot == 0 && *sTilesDone < my_tiles) __nanosleep(50);
+            {
+                const long long t_end = clock64() + 40000;
+                bool all = false;
+                while (!all && clock64() < t_end) {
+                    exchange_publish(sink, p.nq, my_row);
+                    const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot, p.k);
+                    if (lane == 0 && lo != 0u) atomicMax(p.gtau + p.q0 + rq, lo);
+                    bool mine_ok = true;
+                    for (int q = lane; q < p.nq; q += 32) {
+                        const uint32_t g = ld_cg_u32(p.gtau + p.q0 + q);
+                        exchange_apply(sink, q, g);
+                        mine_ok = mine_ok && (g != 0u);
+                    }
+                    all = __all_sync(0xffffffffu, mine_ok);
+                }
+                __syncwarp();
+                if (lane == 0) *sBoot = 2;
+            }
             while (*sTilesDone < my_tiles) {
                 exchange_publish(sink, p.nq, my_row);
                 const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot, p.k);
