@@ -36,6 +36,9 @@ WORKLOADS = {
     "c2": (1_000_000, 768, 64, 100, "cosine"),
     "c2mse": (1_000_000, 768, 64, 100, "MSE"),
     "small": (100_000, 768, 64, 100, "cosine"),
+    # the reference's own regime: one query (Q=1), and the widest single SIMT pass (Q=4)
+    "q1": (1_000_000, 768, 1, 100, "cosine"),
+    "q4": (1_000_000, 768, 4, 100, "cosine"),
 }
 
 
@@ -200,11 +203,11 @@ def run_reference(args, wl):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def build_bank(n_rows, D, dev, row0_chunk=0):
+def build_bank(n_rows, D, dev, row0_chunk=0, dtype="bf16"):
     """Device-generated synthetic shard: chunks [row0_chunk, ...) of the global synthetic bank,
     normalised with the statistics of the first 512 rows of global chunk 0 on every rank."""
     from sky_embeddings_b200 import Bank, synth
-    bank = Bank(n_rows, 1, D, "bf16", dev)
+    bank = Bank(n_rows, 1, D, dtype, dev)
     first = synth.device_bank_chunk(0, 512, D, dev)
     bank.fit_norm(first)
     done = 0
@@ -235,23 +238,30 @@ def run_gpu(args, wl):
     n_bank, D, Q, k, metric = wl
     chunks_per_rank = (n_bank + synth.CHUNK_ROWS - 1) // synth.CHUNK_ROWS
     row_lo = rank * n_bank
-    bank = build_bank(n_bank, D, dev, row0_chunk=rank * chunks_per_rank)
+    bank = build_bank(n_bank, D, dev, row0_chunk=rank * chunks_per_rank, dtype=args.bank_dtype)
+    esz = 2 if args.bank_dtype == "bf16" else 4
 
     # queries: planted neighbours of rows of THIS process's rank-0 shard layout (same on every rank:
     # generated from global chunk 0 with the shared statistics)
     probe = build_bank(min(n_bank, synth.CHUNK_ROWS), D, dev, row0_chunk=0)
     stride = probe.n_items // Q
+    use_tc = args.path == "tensor" or (args.path == "auto" and Q >= 2 and args.bank_dtype == "bf16" and not args.weighted)
     gen = torch.Generator(device=dev).manual_seed(1234)
     planted = [q * stride + stride // 2 for q in range(Q)]
     t_dev = torch.cat([probe.download(r, 1)[:, 0] for r in planted])
     t_dev = t_dev + 0.1 * torch.randn((Q, D), generator=gen, device=dev)
     probe.close()
+    w_dev = None
+    if args.weighted:     # per-query inverse-variance-like weights, normalised to sum 1 (utils/similarity.py:143-145)
+        w_dev = torch.rand((Q, D), generator=gen, device=dev) + 0.5
+        w_dev = w_dev / w_dev.sum(1, keepdim=True)
+    w_host = w_dev.cpu().pin_memory() if w_dev is not None else None
     t_host = t_dev.cpu().pin_memory()
     out_s_host = torch.empty((Q, k), dtype=torch.float32).pin_memory()
     out_i_host = torch.empty((Q, k), dtype=torch.int64).pin_memory()
 
     def step_device():
-        s, i = bank.search(t_dev, None, k=k, metric=metric, path=args.path, idx_offset=row_lo)
+        s, i = bank.search(t_dev, w_dev, k=k, metric=metric, path=args.path, idx_offset=row_lo)
         if world > 1:
             gs, gi = gather_candidates(s, i)
             s, i = merge_candidates(gs, gi, k, metric)
@@ -260,10 +270,11 @@ def run_gpu(args, wl):
     def step_host():
         # public API with HOST buffers: H2D of the queries and D2H of the results inside the call
         if world == 1:
-            return bank.search_host(t_host, None, k=k, metric=metric, path=args.path, idx_offset=row_lo,
+            return bank.search_host(t_host, w_host, k=k, metric=metric, path=args.path, idx_offset=row_lo,
                                     out_scores=out_s_host, out_idx=out_i_host)
         td = t_host.to(dev, non_blocking=True)
-        s, i = bank.search(td, None, k=k, metric=metric, path=args.path, idx_offset=row_lo)
+        wd = w_host.to(dev, non_blocking=True) if w_host is not None else None
+        s, i = bank.search(td, wd, k=k, metric=metric, path=args.path, idx_offset=row_lo)
         gs, gi = gather_candidates(s, i)
         s, i = merge_candidates(gs, gi, k, metric)
         out_s_host.copy_(s, non_blocking=True)
@@ -339,29 +350,29 @@ def run_gpu(args, wl):
     if rank == 0:
         peak, peak_src = read_peaks()
         kern_avg_ms = kern_ms / max(n_kern, 1)
-        algo_bytes = float(n_bank) * D * 2                      # one pass over this GPU's bf16 shard
+        algo_bytes = float(n_bank) * D * esz                    # one pass over this GPU's shard
         achieved = algo_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else 0.0
         value = world * Q / (ms_step * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {n_bank}-vector x {D} bf16 bank per GPU ({n_bank * world} total), "
+            "vs_baseline": None, "dtype": args.bank_dtype, "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n_bank}-vector x {D} {args.bank_dtype} bank per GPU ({n_bank * world} total), "
                                    f"{Q} queries, {metric} top-{k}, exact",
                        "bank_vectors_per_gpu": n_bank, "bank_vectors": n_bank * world, "dim": D, "queries": Q, "k": k,
-                       "similarity": metric, "path": args.path, "parallelism": f"row-shard x{world}",
+                       "similarity": metric, "weighted": bool(args.weighted), "path": args.path, "parallelism": f"row-shard x{world}",
                        "l2_policy": f"bank shard ({algo_bytes / 1e6:.0f} MB) is larger than the 126 MB L2; no flush needed",
                        "value_definition": "N_gpus * Q / step time (query-over-1M-vector-shard searches/s; at N=1 plain QPS)"},
             "qps_global_bank": Q / (ms_step * 1e-3),
             "clocks": sampler.summary(),
             "e2e": {"value": world * Q / (e2e_step * 1e-3), "unit": "queries/s", "ms_per_step": e2e_step,
-                    "h2d_bytes_per_step": t_host.numel() * 4, "d2h_bytes_per_step": Q * k * 12,
+                    "h2d_bytes_per_step": t_host.numel() * 4 * (2 if args.weighted else 1), "d2h_bytes_per_step": Q * k * 12,
                     "api": "sky_search_host (C ABI, pinned host buffers)" if world == 1 else
                            "pinned H2D + sky_search + NCCL all-gather + sky_merge_candidates + D2H"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": read_traffic(args.path),
-                         "kernel": "tc_search_kernel<64>" if args.path != "simt" else "simt_search_kernel",
+                         "frac": achieved / peak if peak else None, "traffic": read_traffic("tensor" if use_tc else "simt"),
+                         "kernel": "tc_search_kernel<64>" if use_tc else "stream_search_kernel",
                          "kernel_ms": kern_avg_ms, "kernel_launches": n_kern, "algorithmic_bytes": algo_bytes,
                          "peak_source": peak_src, "kernel_share_of_step": kern_avg_ms * (n_kern / args.steps) / ms_step},
         }
@@ -383,6 +394,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor"])
+    ap.add_argument("--bank-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--weighted", action="store_true", help="per-query feature weights (use_weights=True)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

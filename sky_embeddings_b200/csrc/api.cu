@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary of libskysearch.so (see include/sky_search.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -261,6 +262,8 @@ int sky_bank_finalize(sky_bank_t* b, void* stream) {
 /* debug only (not part of the public header): timeline of the tensor kernel, see tc_search.cu */
 __attribute__((visibility("default"))) int sky_debug_trace(unsigned long long* h_out, int n) { return debug_read_trace(h_out, n); }
 
+__attribute__((visibility("default"))) int sky_debug_stream_stats(unsigned long long* h_out, int reset) { return debug_stream_stats(h_out, reset); }
+
 __attribute__((visibility("default"))) int sky_debug_epi(unsigned long long* h_out) { return debug_read_epi(h_out); }
 
 int sky_profile_enable(sky_bank_t* b, int enable) {
@@ -333,7 +336,7 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
     if (path == SKY_PATH_TENSOR && !tc_ok)
         return set_error(SKY_ERR_UNSUPPORTED, "tensor path needs a bf16 bank, L=1, cosine/MSE, no weights, no n_top_sims");
     // small query batches stay on the streaming SIMT kernel (HBM bound there); larger ones need MMA
-    const bool use_tc = tc_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q > 4));
+    const bool use_tc = tc_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q >= 2));
 
     SearchState s;
     int rc;
@@ -348,21 +351,34 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
         rc = launch_tc_search(b, t, Q, metric, s, st);
         if (rc) return rc;
     } else {
-        const int qc = (Q == 1) ? 1 : simt_pick_qc(b->Dp);
-        int grid = 1;
-        size_t smem = 0;
-        rc = simt_grid(b, metric, b->L, b->n_items, qc, n_top_sims, &grid, &smem);
-        if (rc) return rc;
-        rc = plan_state(b, grid, Q, k, grid, &s);
-        if (rc) return rc;
-        rc = launch_init_state(s, grid, st);
-        if (rc) return rc;
         SimtArgs a;
         a.bank = b->data; a.dtype = b->dtype; a.row0 = 0; a.n_items = b->n_items; a.L = b->L; a.D = b->D; a.Dp = b->Dp;
         a.t = t; a.w = w; a.Q = Q; a.metric = metric; a.combine = combine; a.n_top = n_top_sims;
         a.emit = nullptr; a.item0 = 0; a.n = 0;
-        rc = launch_simt_search(b, a, s, grid, qc, smem, st);
-        if (rc) return rc;
+        const int sqc = stream_pick_qc(Q);
+        if (path != SKY_PATH_GENERIC && b->rows > 0 && stream_supported(b, sqc)) {
+            // K1: bulk-copy staged streaming scorer
+            const int grid = stream_grid(b, 0, b->rows);
+            rc = plan_state(b, grid, Q, k, grid, &s);
+            if (rc) return rc;
+            rc = launch_init_state(s, grid, st);
+            if (rc) return rc;
+            rc = launch_stream_search(b, a, s, grid, sqc, st);
+            if (rc) return rc;
+        } else {
+            // generic CUDA-core scorer: any L, any D
+            const int qc = (Q == 1) ? 1 : simt_pick_qc(b->Dp);
+            int grid = 1;
+            size_t smem = 0;
+            rc = simt_grid(b, metric, b->L, b->n_items, qc, n_top_sims, &grid, &smem);
+            if (rc) return rc;
+            rc = plan_state(b, grid, Q, k, grid, &s);
+            if (rc) return rc;
+            rc = launch_init_state(s, grid, st);
+            if (rc) return rc;
+            rc = launch_simt_search(b, a, s, grid, qc, smem, st);
+            if (rc) return rc;
+        }
     }
     return launch_merge_lists(s, metric, idx_offset, out_scores, out_idx, st);
 }
@@ -414,17 +430,21 @@ int sky_score(sky_bank_t* b, const float* t, const float* w, int Q, int metric, 
     if (n_items == 0) return SKY_OK;
     DeviceGuard g(b->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int qc = (Q == 1) ? 1 : simt_pick_qc(b->Dp);
-    int grid = 1;
-    size_t smem = 0;
-    int rc = simt_grid(b, metric, b->L, n_items, qc, n_top_sims, &grid, &smem);
-    if (rc) return rc;
     SimtArgs a;
     a.bank = b->data; a.row0 = item0 * b->L;
     a.dtype = b->dtype; a.n_items = n_items; a.L = b->L; a.D = b->D; a.Dp = b->Dp;
     a.t = t; a.w = w; a.Q = Q; a.metric = metric; a.combine = combine; a.n_top = n_top_sims;
     a.emit = out_scores; a.item0 = 0; a.n = n_items;
     SearchState s;   // unused in emit mode
+    const int sqc = stream_pick_qc(Q);
+    static const char* force_generic = getenv("SKY_SCORE_GENERIC");
+    if (!force_generic && stream_supported(b, sqc))
+        return launch_stream_search(b, a, s, stream_grid(b, a.row0, a.row0 + n_items * b->L), sqc, st);
+    const int qc = (Q == 1) ? 1 : simt_pick_qc(b->Dp);
+    int grid = 1;
+    size_t smem = 0;
+    int rc = simt_grid(b, metric, b->L, n_items, qc, n_top_sims, &grid, &smem);
+    if (rc) return rc;
     return launch_simt_search(b, a, s, grid, qc, smem, st);
 }
 

@@ -83,6 +83,13 @@ int simt_pick_qc(int Dp);
 int launch_simt_search(const sky_bank* b, const SimtArgs& a, const SearchState& s, int grid, int qc, size_t smem,
                        cudaStream_t st);
 
+// stream_search.cu
+int stream_pick_qc(int Q);
+bool stream_supported(const sky_bank* b, int qc);
+int stream_grid(const sky_bank* b, int64_t row_lo, int64_t row_hi);
+int debug_stream_stats(unsigned long long* h_out, int reset);
+int launch_stream_search(const sky_bank* b, const SimtArgs& a, const SearchState& s, int grid, int qc, cudaStream_t st);
+
 // tc_search.cu
 bool tc_supported(const sky_bank* b, int metric, bool weighted, int n_top);
 int tc_grid(const sky_bank* b);

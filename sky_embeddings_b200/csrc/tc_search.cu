@@ -347,15 +347,18 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
             uint32_t* my_row = p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0;
             const int rq = static_cast<int>(blockIdx.x) % p.nq;
             int round = 0;
+            uint32_t last_pub[BN / 32] = {};     // keys already published (only changes are rewritten)
+            uint32_t last_lo = 0;                // bound this CTA last contributed for its column
             // bootstrap: wait for the tile-0 maxima, then trade them until every query has a bound
             while (*sBoot == 0 && *sTilesDone < my_tiles) __nanosleep(50);
             {
                 const long long t_end = clock64() + 40000;
                 bool all = false;
                 while (!all && clock64() < t_end) {
-                    exchange_publish(sink, p.nq, my_row);
+                    exchange_publish_changed(sink, p.nq, my_row, last_pub);
                     const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot, p.k);
-                    if (lane == 0 && lo != 0u) atomicMax(p.gtau + p.q0 + rq, lo);
+                    if (lane == 0 && lo > last_lo) atomicMax(p.gtau + p.q0 + rq, lo);
+                    last_lo = lo > last_lo ? lo : last_lo;
                     bool mine_ok = true;
                     for (int q = lane; q < p.nq; q += 32) {
                         const uint32_t g = ld_cg_u32(p.gtau + p.q0 + q);
@@ -368,9 +371,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
                 if (lane == 0) *sBoot = 2;
             }
             while (*sTilesDone < my_tiles) {
-                exchange_publish(sink, p.nq, my_row);
+                exchange_publish_changed(sink, p.nq, my_row, last_pub);
                 const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot, p.k);
-                if (lane == 0 && lo != 0u) atomicMax(p.gtau + p.q0 + rq, lo);
+                if (lane == 0 && lo > last_lo) atomicMax(p.gtau + p.q0 + rq, lo);
+                last_lo = lo > last_lo ? lo : last_lo;
                 for (int q = lane; q < p.nq; q += 32) exchange_apply(sink, q, ld_cg_u32(p.gtau + p.q0 + q));
                 ++round;
                 __nanosleep(round < 24 ? 100 : 3000);

@@ -225,6 +225,20 @@ __device__ __forceinline__ void exchange_publish(const Sink& s, int nq, uint32_t
         if (mine) st_cg_u32(gtop_row + q, mine);
     }
 }
+// same, but only keys that changed since the last call are rewritten (last[i] <-> query lane + 32 i): the
+// entries of all CTAs share a few L2 lines, and rewriting them every round makes those lines a hot spot
+// that delays the bank stream queued behind it
+template <int N>
+__device__ __forceinline__ void exchange_publish_changed(const Sink& s, int nq, uint32_t* gtop_row, uint32_t (&last)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int q = (threadIdx.x & 31) + 32 * i;
+        if (q < nq) {
+            const uint32_t mine = lds_u32(s.lmax + q * 4);
+            if (mine != last[i]) { st_cg_u32(gtop_row + q, mine); last[i] = mine; }
+        }
+    }
+}
 // one warp: k-th largest (1-based) of one query column of gtop; p_stride <= 32 * kMaxPerLane
 constexpr int kXchgPerLane = 32;   // up to 1024 CTAs
 __device__ __forceinline__ uint32_t exchange_reduce(const uint32_t* gtop_col, int p_stride, int q_stride, int k) {

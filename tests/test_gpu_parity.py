@@ -49,13 +49,15 @@ def _engine_simsearch(dev, bank_lat, tgt, bs, k, dtype, path="auto", **kw):
     return out
 
 
+@pytest.mark.parametrize("path", ["auto", "generic"])
 @pytest.mark.parametrize("dtype,rel", [("fp32", REL_F32), ("bf16", REL_BF16_VS_F32_INPUT)])
-def test_golden_simsearch_all_modes(dev, dtype, rel):
+def test_golden_simsearch_all_modes(dev, dtype, rel, path):
+    """auto = the bulk-copy staged streaming scorer (K1); generic = the any-L CUDA-core scorer."""
     g = G.load("simsearch_small")
     bank, tgt, bs, k = G.simsearch_inputs(g)
     for name in g["names"]:
         kw = G.parse_simsearch_name(str(name))
-        sc, ix = _engine_simsearch(dev, bank, tgt, bs, k, dtype, **kw)
+        sc, ix = _engine_simsearch(dev, bank, tgt, bs, k, dtype, path=path, **kw)
         ref_all = None
         if dtype == "bf16":
             # boundary swaps between near-ties are legal at bf16 tolerance: supply all scores
@@ -250,12 +252,14 @@ def test_tensor_path_vs_oracle(dev, metric, n, Q, k):
     bank.close()
 
 
+@pytest.mark.parametrize("path,L", [("auto", 8), ("generic", 8), ("auto", 64), ("auto", 5), ("auto", 1)])
 @pytest.mark.parametrize("dtype,rel", [("fp32", REL_F32), ("bf16", REL_F32)])
-def test_multi_query_weighted_patches(dev, dtype, rel):
-    """Q > 1 with per-query weights, L = 8 patches, every combine, n_top_sims: oracle = reference per query.
-    (bf16 bank: the oracle sees the stored values, so fp32 tolerance applies to the arithmetic.)"""
+def test_multi_query_weighted_patches(dev, dtype, rel, path, L):
+    """Q > 1 with per-query weights, L patches, every combine, n_top_sims: oracle = reference per query.
+    (bf16 bank: the oracle sees the stored values, so fp32 tolerance applies to the arithmetic.)
+    L = 8 / 64 / 1 run on the streaming scorer, L = 5 (does not divide a row block) on the generic one."""
     from sky_embeddings_b200 import Bank, synth
-    n, L, D, Q, k = 1500, 8, 96, 7, 25
+    n, D, Q, k = (1500 if L <= 8 else 400), 96, 7, 25
     lat = synth.latents(n, L, D, stream=111)
     bank = Bank.from_latents(torch.from_numpy(lat).to(dev), norm_rows=32, dtype=dtype)
     z = bank.download().cpu().numpy().astype(np.float64)
@@ -270,8 +274,8 @@ def test_multi_query_weighted_patches(dev, dtype, rel):
     tn, wn = t.cpu().numpy().astype(np.float64), w.cpu().numpy().astype(np.float64)
     for metric in ("cosine", "MSE", "MAE"):
         for combine in ("mean", "min", "max"):
-            for nts in (None, 3):
-                sc, ix = bank.search(t, w, k=k, metric=metric, combine=combine, n_top_sims=nts)
+            for nts in ((None, 3) if L >= 3 else (None,)):
+                sc, ix = bank.search(t, w, k=k, metric=metric, combine=combine, n_top_sims=nts, path=path)
                 ref_s, ref_i = O.search(tn, wn, z, k, metric, combine, nts)
                 for q in range(Q):
                     ok, msg = O.check_topk_parity(sc[q].cpu().numpy(), ix[q].cpu().numpy(), ref_s[q], ref_i[q], rel)
