@@ -129,6 +129,22 @@ SKY_API int sky_search_host(sky_bank_t* bank, const float* h_t, const float* h_w
 SKY_API int sky_score(sky_bank_t* bank, const float* t, const float* w, int Q, int metric, int combine,
               int n_top_sims, int64_t item0, int64_t n_items, float* out_scores, void* stream);
 
+/* ---- pixel-space masked-MSE search (BASELINE config 5) -----------------------------------------
+ * The reference has no pixel-space search; SURVEY.md section 8(d) defines it from the reference's
+ * weighted_MSE (utils/similarity.py:174-192) with the weights replaced by a validity mask and the
+ * NaN handling / normaliser of the MAE loss (utils/mim_vit.py:482-486, :509-519):
+ *   valid = ~isnan(q) & ~isnan(x);  m = valid * qmask;  score = sum m (q-x)^2 / (sum m + 1e-5), ascending.
+ * The bank holds raw cutouts [n_items, C, H, W] fp32 with their NaNs (cutouts / ra / dec layout of
+ * data_processing/utils.py:346-350); it is a sky_bank_t handle (destroy / info / resize / download /
+ * profile apply; the embedding calls refuse it).  src of upload may be a device or host pointer. */
+SKY_API int sky_pixel_bank_create(sky_bank_t** bank, int device, int64_t n_items, int C, int H, int W);
+SKY_API int sky_pixel_bank_upload(sky_bank_t* bank, const float* src, int64_t item0, int64_t n_items, void* stream);
+/* q[Q, C*H*W] f32 (NaN = missing), qmask[Q, C*H*W] u8 (1 = compare) or NULL = all ones. */
+SKY_API int sky_search_pixels(sky_bank_t* bank, const float* q, const unsigned char* qmask, int Q, int k,
+                      int64_t idx_offset, float* out_scores, int64_t* out_idx, void* stream);
+SKY_API int sky_score_pixels(sky_bank_t* bank, const float* q, const unsigned char* qmask, int Q, int64_t item0,
+                     int64_t n_items, float* out_scores, void* stream);
+
 /* merge R candidate lists per query into one top-k_out, best first: the shard merge after the
  * NCCL all-gather, and the running merge of update_best_scores (utils/similarity.py:18-35).
  * scores[R,Q,k_in] f32, idx[R,Q,k_in] i64 (idx < 0 = empty slot). */

@@ -204,6 +204,39 @@ def update_best_cases(ref):
     return out
 
 
+def pixel_cases(ref):
+    """Pixel-space masked MSE: the reference has no pixel search, so its
+    weighted_MSE (utils/similarity.py:174-192) is driven row by row with w = validity mask on NaN-zeroed
+    tensors; weighted_MSE * D = sum m (q-x)^2 / sum m, the definition up to the 1e-5 in the normaliser."""
+    out = {}
+    seed = synth.BASE_SEED
+    n, C, H, W, Q = 40, 5, 16, 16, 3
+    x = synth.cutouts(n, C, H, W, seed=seed, stream=51)
+    q = synth.cutouts(Q, C, H, W, seed=seed, stream=52, nan_frac=0.01, nan_chan_p=0.2)
+    rng = np.random.Generator(np.random.PCG64([seed, 53]))
+    qmask = (rng.random((Q, C, H, W)) < 0.6).astype(np.uint8)
+    qmask[0] = 1                                    # query 0: no patch mask
+    x[7] = np.nan                                   # a cutout with nothing valid
+    out["meta"] = np.array([n, C, H, W, Q, seed, 51, 52, 53], dtype=np.int64)
+    out["checksum"] = np.array(checksum(x, q, qmask))
+    D = C * H * W
+    ratio = np.zeros((Q, n), dtype=np.float64)      # sum m (q-x)^2 / sum m   from the reference
+    msum = np.zeros((Q, n), dtype=np.float64)
+    for qi in range(Q):
+        qf = torch.from_numpy(q[qi].reshape(-1))
+        for r in range(n):
+            xf = torch.from_numpy(x[r].reshape(-1))
+            m = (~torch.isnan(qf)) & (~torch.isnan(xf)) & torch.from_numpy(qmask[qi].reshape(-1) != 0)
+            q0, x0 = torch.nan_to_num(qf, nan=0.0).double(), torch.nan_to_num(xf, nan=0.0).double()
+            msum[qi, r] = float(m.sum())
+            if m.any():
+                v = ref.weighted_MSE(q0, x0[None, None], m.double())      # [1, 1]
+                ratio[qi, r] = float(v[0, 0]) * D
+    out["ratio"] = ratio
+    out["msum"] = msum
+    return out
+
+
 def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -211,7 +244,7 @@ def main():
     torch.set_num_threads(1)   # deterministic reduction order for the fixtures
     for name, fn in (("simsearch_small", simsearch_cases), ("simsearch_mim1_shape", mim1_shape_case),
                      ("short_bank", short_bank_case), ("compute_similarity", compute_similarity_cases),
-                     ("update_best", update_best_cases)):
+                     ("update_best", update_best_cases), ("pixel_small", pixel_cases)):
         data = fn(ref)
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **data)

@@ -7,11 +7,11 @@ teaghan/sky_embeddings (utils/similarity.py as driven by similarity_search.py / 
 Everything numeric runs in libskysearch.so (hand-written sm_100a CUDA behind a C ABI,
 include/sky_search.h); importing the search API without the built library raises.
 """
-__all__ = ["Bank", "merge_candidates", "ShardedBank", "sharded_search", "shard_range"]
+__all__ = ["Bank", "PixelBank", "merge_candidates", "ShardedBank", "sharded_search", "shard_range"]
 
 
 def __getattr__(name):
-    if name in ("Bank", "merge_candidates"):
+    if name in ("Bank", "PixelBank", "merge_candidates"):
         from . import engine
         return getattr(engine, name)
     if name in ("ShardedBank", "sharded_search", "shard_range"):

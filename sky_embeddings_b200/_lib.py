@@ -40,6 +40,10 @@ SIGNATURES = {
     "sky_search": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _i, _vp]),
     "sky_search_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _i, _vp]),
     "sky_score": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp, _vp]),
+    "sky_pixel_bank_create": (_i, [C.POINTER(_vp), _i, _i64, _i, _i, _i]),
+    "sky_pixel_bank_upload": (_i, [_vp, _vp, _i64, _i64, _vp]),
+    "sky_search_pixels": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]),
+    "sky_score_pixels": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _vp]),
     "sky_merge_candidates": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sky_profile_enable": (_i, [_vp, _i]),
     "sky_profile_read": (_i, [_vp, C.POINTER(_i64), C.POINTER(C.c_double), _i]),

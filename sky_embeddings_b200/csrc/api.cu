@@ -238,6 +238,7 @@ int sky_bank_upload(sky_bank_t* b, const void* src, int src_dtype, int64_t item0
     if (src_dtype != SKY_F32 && src_dtype != SKY_BF16) return set_error(SKY_ERR_ARG, "bad source dtype %d", src_dtype);
     if (item0 < 0 || n_items < 0 || item0 + n_items > b->n_items)
         return set_error(SKY_ERR_ARG, "items [%lld, %lld) outside the bank (%lld items)", (long long)item0, (long long)(item0 + n_items), (long long)b->n_items);
+    if (b->pixel) return set_error(SKY_ERR_STATE, "this is a pixel bank: use sky_pixel_bank_upload");
     if (token_out(token_mode, src_tokens, num_extra_tokens) != b->L)
         return set_error(SKY_ERR_ARG, "token selection yields %d tokens, bank expects L=%d", token_out(token_mode, src_tokens, num_extra_tokens), b->L);
     DeviceGuard g(b->device);
@@ -250,6 +251,7 @@ int sky_bank_upload(sky_bank_t* b, const void* src, int src_dtype, int64_t item0
 int sky_bank_finalize(sky_bank_t* b, void* stream) {
     (void)stream;
     if (!b) return set_error(SKY_ERR_ARG, "bank is NULL");
+    if (b->pixel) return SKY_OK;
     DeviceGuard g(b->device);
     if (b->dtype == SKY_BF16 && !b->tmap_ready) {
         int rc = tc_make_bank_tmap(b);
@@ -308,6 +310,12 @@ int sky_bank_download(const sky_bank_t* b, int64_t item0, int64_t n_items, float
     if (!b || !dst) return set_error(SKY_ERR_ARG, "NULL argument");
     if (item0 < 0 || n_items < 0 || item0 + n_items > b->n_items) return set_error(SKY_ERR_ARG, "item range outside the bank");
     DeviceGuard g(b->device);
+    if (b->pixel) {
+        SKY_CUDA(cudaMemcpyAsync(dst, reinterpret_cast<const float*>(b->data) + static_cast<size_t>(item0) * b->D,
+                                 static_cast<size_t>(n_items) * b->D * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+        return SKY_OK;
+    }
     return launch_download(b->data, b->dtype, item0 * b->L, n_items * b->L, b->D, b->Dp, dst, static_cast<cudaStream_t>(stream));
 }
 
@@ -331,6 +339,7 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
     if (!valid_combine(combine)) return set_error(SKY_ERR_ARG, "unknown combine %d", combine);
     if (Q < 1 || k < 1) return set_error(SKY_ERR_ARG, "Q and k must be positive");
     if (n_top_sims < 0 || n_top_sims > b->L) return set_error(SKY_ERR_ARG, "n_top_sims=%d out of range for L=%d", n_top_sims, b->L);
+    if (b->pixel) return set_error(SKY_ERR_STATE, "this is a pixel bank: use sky_search_pixels");
     if (!b->finalized) return set_error(SKY_ERR_STATE, "bank is not finalized");
     const bool tc_ok = tc_supported(b, metric, w != nullptr, n_top_sims);
     if (path == SKY_PATH_TENSOR && !tc_ok)
@@ -427,6 +436,7 @@ int sky_score(sky_bank_t* b, const float* t, const float* w, int Q, int metric, 
     if (Q < 1) return set_error(SKY_ERR_ARG, "Q must be positive");
     if (n_top_sims < 0 || n_top_sims > b->L) return set_error(SKY_ERR_ARG, "n_top_sims=%d out of range for L=%d", n_top_sims, b->L);
     if (item0 < 0 || n_items < 0 || item0 + n_items > b->n_items) return set_error(SKY_ERR_ARG, "item range outside the bank");
+    if (b->pixel) return set_error(SKY_ERR_STATE, "this is a pixel bank: use sky_score_pixels");
     if (n_items == 0) return SKY_OK;
     DeviceGuard g(b->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -446,6 +456,97 @@ int sky_score(sky_bank_t* b, const float* t, const float* w, int Q, int metric, 
     int rc = simt_grid(b, metric, b->L, n_items, qc, n_top_sims, &grid, &smem);
     if (rc) return rc;
     return launch_simt_search(b, a, s, grid, qc, smem, st);
+}
+
+/* ---- pixel-space bank (BASELINE config 5) ---------------------------------------------------- */
+int sky_pixel_bank_create(sky_bank_t** out, int device, int64_t n_items, int C, int H, int W) {
+    if (!out) return set_error(SKY_ERR_ARG, "bank out-pointer is NULL");
+    *out = nullptr;
+    if (n_items < 0 || C < 1 || H < 1 || W < 1) return set_error(SKY_ERR_ARG, "bad pixel bank shape");
+    const int64_t D = static_cast<int64_t>(C) * H * W;
+    if (D % 4 != 0 || D > (1 << 24)) return set_error(SKY_ERR_UNSUPPORTED, "C*H*W = %lld must be a multiple of 4 (and < 2^24)", (long long)D);
+    if (n_items >= 0xFFFFFFFFll) return set_error(SKY_ERR_UNSUPPORTED, "a bank shard is limited to 2^32-2 rows");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_error(SKY_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return set_error(SKY_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return set_error(SKY_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return set_error(SKY_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return set_error(SKY_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+    sky_bank* b = new (std::nothrow) sky_bank();
+    if (!b) return set_error(SKY_ERR_NOMEM, "host allocation failed");
+    b->device = device; b->num_sms = prop.multiProcessorCount;
+    b->pixel = true; b->n_items = n_items; b->capacity = n_items; b->L = 1; b->D = static_cast<int>(D); b->Dp = b->D;
+    b->dtype = SKY_F32; b->rows = n_items; b->rows_pad = n_items;
+    const size_t data_b = static_cast<size_t>(n_items > 0 ? n_items : 1) * D * sizeof(float);
+    cudaError_t e = cudaMalloc(&b->data, data_b);
+    if (e != cudaSuccess) {
+        int rc = set_error(SKY_ERR_NOMEM, "pixel bank allocation of %zu B failed: %s", data_b, cudaGetErrorString(e));
+        sky_bank_destroy(b);
+        return rc;
+    }
+    b->finalized = true;
+    *out = b;
+    return SKY_OK;
+}
+
+int sky_pixel_bank_upload(sky_bank_t* b, const float* src, int64_t item0, int64_t n_items, void* stream) {
+    if (!b || (!src && n_items > 0)) return set_error(SKY_ERR_ARG, "NULL argument");
+    if (!b->pixel) return set_error(SKY_ERR_STATE, "not a pixel bank");
+    if (item0 < 0 || n_items < 0 || item0 + n_items > b->n_items) return set_error(SKY_ERR_ARG, "item range outside the bank");
+    DeviceGuard g(b->device);
+    // src may be a device or a (pinned / pageable) host pointer: the copy kind is resolved by the runtime
+    SKY_CUDA(cudaMemcpyAsync(reinterpret_cast<float*>(b->data) + static_cast<size_t>(item0) * b->D, src,
+                             static_cast<size_t>(n_items) * b->D * sizeof(float), cudaMemcpyDefault,
+                             static_cast<cudaStream_t>(stream)));
+    return SKY_OK;
+}
+
+static int pixel_impl(sky_bank_t* b, const float* q, const unsigned char* qmask, int Q, int k, int64_t idx_offset,
+                      float* out_scores, int64_t* out_idx, int64_t item0, int64_t n_items, float* emit, cudaStream_t st) {
+    if (!b || !q) return set_error(SKY_ERR_ARG, "NULL argument");
+    if (!b->pixel) return set_error(SKY_ERR_STATE, "not a pixel bank");
+    if (Q < 1) return set_error(SKY_ERR_ARG, "Q must be positive");
+    const int64_t nq = static_cast<int64_t>(Q) * b->D;
+    int rc = ensure_ws2(b, static_cast<size_t>(nq) * sizeof(float) + 256);
+    if (rc) return rc;
+    float* qp = reinterpret_cast<float*>(b->ws2);
+    rc = launch_pixel_fold(q, qmask, nq, qp, st);
+    if (rc) return rc;
+    const int qc = pixel_pick_qc(Q);
+    SearchState s;
+    if (emit) {
+        if (n_items == 0) return SKY_OK;
+        return launch_pixel_search(b, qp, Q, item0, item0 + n_items, s, pixel_grid(b, n_items), qc, emit, st);
+    }
+    const int grid = pixel_grid(b, b->rows);
+    rc = plan_state(b, grid, Q, k, grid, &s);
+    if (rc) return rc;
+    rc = launch_init_state(s, grid, st);
+    if (rc) return rc;
+    if (b->rows > 0) {
+        rc = launch_pixel_search(b, qp, Q, 0, b->rows, s, grid, qc, nullptr, st);
+        if (rc) return rc;
+    }
+    return launch_merge_lists(s, SKY_MSE, idx_offset, out_scores, out_idx, st);
+}
+
+int sky_search_pixels(sky_bank_t* b, const float* q, const unsigned char* qmask, int Q, int k, int64_t idx_offset,
+                      float* out_scores, int64_t* out_idx, void* stream) {
+    if (!b || !out_scores || !out_idx) return set_error(SKY_ERR_ARG, "NULL argument");
+    if (k < 1) return set_error(SKY_ERR_ARG, "k must be positive");
+    DeviceGuard g(b->device);
+    return pixel_impl(b, q, qmask, Q, k, idx_offset, out_scores, out_idx, 0, 0, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int sky_score_pixels(sky_bank_t* b, const float* q, const unsigned char* qmask, int Q, int64_t item0, int64_t n_items,
+                     float* out_scores, void* stream) {
+    if (!b || !out_scores) return set_error(SKY_ERR_ARG, "NULL argument");
+    if (item0 < 0 || n_items < 0 || item0 + n_items > b->n_items) return set_error(SKY_ERR_ARG, "item range outside the bank");
+    DeviceGuard g(b->device);
+    return pixel_impl(b, q, qmask, Q, 1, 0, nullptr, nullptr, item0, n_items, out_scores, static_cast<cudaStream_t>(stream));
 }
 
 int sky_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int k_out, int metric,

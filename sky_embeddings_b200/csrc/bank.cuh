@@ -24,6 +24,7 @@ struct sky_bank {
     float* sp = nullptr;        // [D] sigma + 1e-8
     bool has_norm = false;
     bool finalized = false;
+    bool pixel = false;         // pixel-space bank: data is row-major [n_items][D] fp32 with NaNs kept
     // grow-only scratch
     void* ws = nullptr;
     size_t ws_bytes = 0;
@@ -89,6 +90,13 @@ bool stream_supported(const sky_bank* b, int qc);
 int stream_grid(const sky_bank* b, int64_t row_lo, int64_t row_hi);
 int debug_stream_stats(unsigned long long* h_out, int reset);
 int launch_stream_search(const sky_bank* b, const SimtArgs& a, const SearchState& s, int grid, int qc, cudaStream_t st);
+
+// pixel_search.cu
+int pixel_pick_qc(int Q);
+int pixel_grid(const sky_bank* b, int64_t n_rows);
+int launch_pixel_fold(const float* q, const unsigned char* mask, int64_t n, float* qp, cudaStream_t st);
+int launch_pixel_search(const sky_bank* b, const float* qp, int Q, int64_t row_lo, int64_t row_hi, const SearchState& s,
+                        int grid, int qc, float* emit, cudaStream_t st);
 
 // tc_search.cu
 bool tc_supported(const sky_bank* b, int metric, bool weighted, int n_top);

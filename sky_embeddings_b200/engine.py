@@ -8,6 +8,7 @@ update_best_scores :18-35).
 from __future__ import annotations
 
 import ctypes as C
+import ctypes as C_
 
 import torch
 
@@ -230,6 +231,91 @@ class Bank:
         L.check(self.lib.sky_score(self._h, _ptr(t), _ptr(w) if w is not None else None, t.shape[0],
                                    L.METRICS[metric], L.COMBINES[combine], int(n_top_sims or 0), int(item0), int(n),
                                    _ptr(out), _stream(self.device)))
+        return out
+
+
+class PixelBank:
+    """Raw cutouts [N, C, H, W] fp32 (NaN = missing pixel / band) resident in HBM, searched in pixel space
+    with the NaN-aware masked MSE of BASELINE config 5:
+    score = sum m (q - x)^2 / (sum m + 1e-5), m = ~isnan(q) & ~isnan(x) & qmask; lower is better."""
+
+    def __init__(self, n_items, C, H, W, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sky_embeddings_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_items, self.shape, self.D = int(n_items), (int(C), int(H), int(W)), int(C) * int(H) * int(W)
+        h = C_.c_void_p()
+        L.check(self.lib.sky_pixel_bank_create(C_.byref(h), self.device.index, self.n_items, *self.shape))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.sky_bank_destroy(self._h)
+            self._h = C_.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, cutouts, item0=0):
+        """cutouts [n, C, H, W] (or [n, D]) float32, on this device or on the host."""
+        x = cutouts.to(torch.float32).contiguous()
+        if x.is_cuda and x.device != self.device:
+            x = x.to(self.device)
+        if x[0].numel() != self.D:
+            raise ValueError(f"expected cutouts of {self.shape}, got {tuple(x.shape[1:])}")
+        L.check(self.lib.sky_pixel_bank_upload(self._h, _ptr(x), int(item0), x.shape[0], _stream(self.device)))
+        if not x.is_cuda:
+            torch.cuda.current_stream(self.device).synchronize()      # the host buffer may go away
+        return self
+
+    @classmethod
+    def from_cutouts(cls, cutouts, device=None, chunk_items=4096):
+        n = cutouts.shape[0]
+        bank = cls(n, *cutouts.shape[1:], device=device)
+        for s in range(0, n, chunk_items):
+            bank.upload(cutouts[s:s + chunk_items], s)
+        return bank
+
+    def profile(self, enable=True):
+        L.check(self.lib.sky_profile_enable(self._h, 1 if enable else 0))
+        return self
+
+    def profile_read(self, reset=True):
+        n, ms = C_.c_int64(), C_.c_double()
+        L.check(self.lib.sky_profile_read(self._h, C_.byref(n), C_.byref(ms), 1 if reset else 0))
+        return int(n.value), float(ms.value)
+
+    def _qprep(self, q, qmask):
+        q = q.to(self.device, torch.float32).reshape(-1, self.D).contiguous() if q.dim() != 1 else \
+            q.to(self.device, torch.float32).reshape(1, self.D).contiguous()
+        if qmask is not None:
+            qmask = (qmask.to(self.device) != 0).to(torch.uint8).reshape(-1, self.D)
+            qmask = qmask.expand(q.shape[0], self.D).contiguous()
+        return q, qmask
+
+    def search(self, q, qmask=None, k=100, idx_offset=0):
+        """q [Q, C, H, W] (NaN = missing), qmask same shape (non-zero = compare) or None.
+        Returns (scores [Q, k] ascending, idx [Q, k] i64)."""
+        q, qmask = self._qprep(q, qmask)
+        Q = q.shape[0]
+        scores = torch.empty((Q, k), device=self.device, dtype=torch.float32)
+        idx = torch.empty((Q, k), device=self.device, dtype=torch.int64)
+        L.check(self.lib.sky_search_pixels(self._h, _ptr(q), _ptr(qmask) if qmask is not None else None, Q, int(k),
+                                           int(idx_offset), _ptr(scores), _ptr(idx), _stream(self.device)))
+        return scores, idx
+
+    def score(self, q, qmask=None, item0=0, n_items=None):
+        q, qmask = self._qprep(q, qmask)
+        n = self.n_items - item0 if n_items is None else n_items
+        out = torch.empty((q.shape[0], n), device=self.device, dtype=torch.float32)
+        L.check(self.lib.sky_score_pixels(self._h, _ptr(q), _ptr(qmask) if qmask is not None else None, q.shape[0],
+                                          int(item0), int(n), _ptr(out), _stream(self.device)))
         return out
 
 

@@ -35,3 +35,15 @@ def parse_simsearch_name(name):
     kw = dict(metric=metric, combine=combine, use_weights=(uw == "w"),
               max_pool=(mode == "maxpool"), cls_token=(mode == "cls"))
     return kw
+
+
+def pixel_inputs(g):
+    n, C, H, W, Q, seed, s_x, s_q, s_m = [int(v) for v in g["meta"]]
+    x = synth.cutouts(n, C, H, W, seed=seed, stream=s_x)
+    q = synth.cutouts(Q, C, H, W, seed=seed, stream=s_q, nan_frac=0.01, nan_chan_p=0.2)
+    rng = np.random.Generator(np.random.PCG64([seed, s_m]))
+    qmask = (rng.random((Q, C, H, W)) < 0.6).astype(np.uint8)
+    qmask[0] = 1
+    x[7] = np.nan
+    assert checksum(x, q, qmask) == str(g["checksum"]), "synthetic generator drifted from the fixtures"
+    return x, q, qmask

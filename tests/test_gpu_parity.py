@@ -456,3 +456,71 @@ def test_config2_shape_property_checks(dev):
                                       ref_i[q].cpu().numpy(), 2e-5)
         assert ok, f"simt q{q}: {msg}"
     bank.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# pixel-space masked MSE (BASELINE config 5): parity vs the restated oracle, itself pinned to the
+# reference's weighted_MSE by tests/golden/pixel_small.npz
+# ------------------------------------------------------------------------------------------------
+REL_PIXEL = 1e-5     # fp32 tolerance of the north star
+
+
+def test_pixel_golden_scores_and_topk(dev):
+    from sky_embeddings_b200 import PixelBank
+    g = G.load("pixel_small")
+    x, q, qmask = G.pixel_inputs(g)
+    bank = PixelBank.from_cutouts(torch.from_numpy(x), device=dev)
+    qt, mt = torch.from_numpy(q).to(dev), torch.from_numpy(qmask).to(dev)
+    got = bank.score(qt, mt).cpu().numpy()
+    want = g["ratio"] * g["msum"] / (g["msum"] + O.PIXEL_EPS)
+    assert O.score_close(got, want, REL_PIXEL, scale=1e-9).all()
+    k = 15
+    sc, ix = bank.search(qt, mt, k=k)
+    for qi in range(q.shape[0]):
+        ref_s, ref_i = O.topk(want[qi], k, "MSE")
+        ok, msg = O.check_topk_parity(sc[qi].cpu().numpy(), ix[qi].cpu().numpy(), ref_s, ref_i, REL_PIXEL, all_scores=want[qi])
+        assert ok, f"q{qi}: {msg}"
+    assert int(ix[0, 0]) == 7 and float(sc[0, 0]) == 0.0      # the all-NaN cutout scores 0 / 1e-5 = 0
+    bank.close()
+
+
+@pytest.mark.parametrize("n,Q,k,use_mask", [(3000, 1, 50, False), (2500, 4, 100, True), (1111, 3, 20, True), (5, 2, 10, False)])
+def test_pixel_full_size_cutouts_vs_oracle(dev, n, Q, k, use_mask):
+    """5 x 64 x 64 cutouts (D = 20480: 5 pieces of 16 KB per row), NaN pixels and missing bands."""
+    from sky_embeddings_b200 import PixelBank, synth
+    x = synth.cutouts(n, 5, 64, 64, stream=61)
+    rng = np.random.Generator(np.random.PCG64([7, n]))
+    rows = rng.integers(0, n, Q)
+    q = x[rows] + 0.2 * rng.standard_normal((Q, 5, 64, 64)).astype(np.float32)       # planted neighbours
+    qmask = (rng.random((Q, 5, 64, 64)) < 0.5).astype(np.uint8) if use_mask else None
+    bank = PixelBank.from_cutouts(torch.from_numpy(x), device=dev, chunk_items=700)
+    sc, ix = bank.search(torch.from_numpy(q).to(dev), None if qmask is None else torch.from_numpy(qmask).to(dev), k=k)
+    sc, ix = sc.cpu().numpy(), ix.cpu().numpy()
+    kk = min(k, n)
+    for qi in range(Q):
+        all_ref = O.pixel_masked_mse(q[qi], x, None if qmask is None else qmask[qi])
+        ref_s, ref_i = O.topk(all_ref, k, "MSE")
+        ok, msg = O.check_topk_parity(sc[qi], ix[qi], ref_s, ref_i, REL_PIXEL, all_scores=all_ref)
+        assert ok, f"n={n} q{qi}: {msg}"
+        assert ix[qi, 0] == rows[qi]
+        if n < k:
+            assert np.all(ix[qi, kk:] == -1) and np.all(np.isposinf(sc[qi, kk:]))
+    bank.close()
+
+
+def test_pixel_odd_row_length_and_subrange(dev):
+    """C*H*W not a multiple of the 4096-element piece (short last piece) and score() on a sub-range."""
+    from sky_embeddings_b200 import PixelBank, synth
+    n, C, H, W = 300, 3, 40, 44          # D = 5280 = 4096 + 1184
+    x = synth.cutouts(n, C, H, W, stream=62)
+    q = synth.cutouts(2, C, H, W, stream=63)
+    bank = PixelBank.from_cutouts(torch.from_numpy(x), device=dev)
+    got = bank.score(torch.from_numpy(q).to(dev), None, item0=37, n_items=201).cpu().numpy()
+    for qi in range(2):
+        want = O.pixel_masked_mse(q[qi], x[37:238])
+        assert O.score_close(got[qi], want, REL_PIXEL, scale=1e-9).all()
+    with pytest.raises(Exception):
+        bank.lib  # noqa: B018
+        from sky_embeddings_b200 import _lib as LL
+        LL.check(bank.lib.sky_bank_finalize(None, None))
+    bank.close()
