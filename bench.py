@@ -39,6 +39,11 @@ WORKLOADS = {
     # the reference's own regime: one query (Q=1), and the widest single SIMT pass (Q=4)
     "q1": (1_000_000, 768, 1, 100, "cosine"),
     "q4": (1_000_000, 768, 4, 100, "cosine"),
+    # BASELINE configs[2] ("C3"): 10M-vector bank, 4096-query batch, L2 (= unweighted MSE), tensor-pipe bound
+    "c3": (10_000_000, 768, 4096, 100, "MSE"),
+    "c3s": (1_000_000, 768, 4096, 100, "MSE"),
+    # BASELINE configs[3] ("C4") per-GPU share at 8 GPUs: 12.5M of 100M vectors, 1000 queries, top-1000
+    "c4": (12_500_000, 768, 1000, 1000, "cosine"),
 }
 
 
@@ -245,7 +250,7 @@ def run_gpu(args, wl):
     # generated from global chunk 0 with the shared statistics)
     probe = build_bank(min(n_bank, synth.CHUNK_ROWS), D, dev, row0_chunk=0)
     stride = probe.n_items // Q
-    use_tc = args.path == "tensor" or (args.path == "auto" and Q >= 2 and args.bank_dtype == "bf16" and not args.weighted)
+    use_tc = args.path in ("tensor", "batch") or (args.path == "auto" and Q >= 2 and args.bank_dtype == "bf16" and not args.weighted)
     gen = torch.Generator(device=dev).manual_seed(1234)
     planted = [q * stride + stride // 2 for q in range(Q)]
     t_dev = torch.cat([probe.download(r, 1)[:, 0] for r in planted])
@@ -352,6 +357,7 @@ def run_gpu(args, wl):
         kern_avg_ms = kern_ms / max(n_kern, 1)
         algo_bytes = float(n_bank) * D * esz                    # one pass over this GPU's shard
         achieved = algo_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else 0.0
+        use_batch = use_tc and (args.path == "batch" or (args.path == "auto" and Q > 128))
         value = world * Q / (ms_step * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -376,6 +382,21 @@ def run_gpu(args, wl):
                          "kernel_ms": kern_avg_ms, "kernel_launches": n_kern, "algorithmic_bytes": algo_bytes,
                          "peak_source": peak_src, "kernel_share_of_step": kern_avg_ms * (n_kern / args.steps) / ms_step},
         }
+        if use_batch:
+            # tensor-pipe bound: all phase launches of one search together; flops = 2 Q N D
+            tf_peak = 1392.2
+            try:
+                tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+            except Exception:
+                pass
+            kern_search_ms = kern_ms / args.steps
+            flops = 2.0 * Q * float(n_bank) * D
+            ach = flops / (kern_search_ms * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                                "traffic": None, "kernel": "tc_batch_kernel (all phases of one search)",
+                                "kernel_ms": kern_search_ms, "kernel_launches": n_kern, "algorithmic_flops": flops,
+                                "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)",
+                                "kernel_share_of_step": kern_search_ms / ms_step}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_block(n_bank, D, Q, k, metric)
         print(json.dumps(line), flush=True)
@@ -516,7 +537,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(PIXEL_WORKLOADS))
-    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor"])
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor", "batch", "generic"])
     ap.add_argument("--bank-dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--weighted", action="store_true", help="per-query feature weights (use_weights=True)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")

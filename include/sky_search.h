@@ -64,6 +64,7 @@ extern "C" {
 #define SKY_PATH_AUTO    0
 #define SKY_PATH_SIMT    1   /* HBM-streaming CUDA-core kernel, bulk-copy staged (any dtype / metric / weights) */
 #define SKY_PATH_TENSOR  2   /* tcgen05 contraction (bf16 bank, cosine / MSE) */
+#define SKY_PATH_BATCH   4   /* GEMM-shaped tcgen05 kernel for large query batches (phased bounds) */
 #define SKY_PATH_GENERIC 3   /* generic CUDA-core kernel (any L, any D); also the fallback of SIMT */
 
 typedef struct sky_bank sky_bank_t;

@@ -15,11 +15,11 @@ F32, BF16 = 0, 1
 COSINE, MSE, MAE = 0, 1, 2
 MEAN, MIN, MAX = 0, 1, 2
 TOK_ALL, TOK_CLS, TOK_PATCHES, TOK_MAXPOOL = 0, 1, 2, 3
-PATH_AUTO, PATH_SIMT, PATH_TENSOR, PATH_GENERIC = 0, 1, 2, 3
+PATH_AUTO, PATH_SIMT, PATH_TENSOR, PATH_GENERIC, PATH_BATCH = 0, 1, 2, 3, 4
 
 METRICS = {"cosine": COSINE, "MSE": MSE, "MAE": MAE}
 COMBINES = {"mean": MEAN, "min": MIN, "max": MAX}
-PATHS = {"auto": PATH_AUTO, "simt": PATH_SIMT, "tensor": PATH_TENSOR, "generic": PATH_GENERIC}
+PATHS = {"auto": PATH_AUTO, "simt": PATH_SIMT, "tensor": PATH_TENSOR, "generic": PATH_GENERIC, "batch": PATH_BATCH}
 
 # every symbol include/sky_search.h declares: (restype, argtypes)
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64

@@ -346,6 +346,12 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
         return set_error(SKY_ERR_UNSUPPORTED, "tensor path needs a bf16 bank, L=1, cosine/MSE, no weights, no n_top_sims");
     // small query batches stay on the streaming SIMT kernel (HBM bound there); larger ones need MMA
     const bool use_tc = tc_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q >= 2));
+    // large query batches: the GEMM-shaped kernel (bank tile reused by all query groups through L2)
+    const bool batch_ok = tc_batch_supported(b, metric, w != nullptr, n_top_sims, k);
+    if (path == SKY_PATH_BATCH && !batch_ok)
+        return set_error(SKY_ERR_UNSUPPORTED, "batched tensor path needs a finalized bf16 bank, L=1, cosine/MSE, no weights, k <= 4096");
+    if (batch_ok && (path == SKY_PATH_BATCH || (path == SKY_PATH_AUTO && Q > 128)))
+        return launch_tc_batch(b, t, Q, metric, k, idx_offset, out_scores, out_idx, st);
 
     SearchState s;
     int rc;

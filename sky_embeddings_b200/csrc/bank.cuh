@@ -107,6 +107,11 @@ size_t tc_scratch_bytes(const sky_bank* b, int Q);
 int debug_read_trace(unsigned long long* h_out, int n);
 int debug_read_epi(unsigned long long* h_out);
 
+// tc_batch.cu
+bool tc_batch_supported(const sky_bank* b, int metric, bool weighted, int n_top, int k);
+int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64_t idx_offset, float* out_scores,
+                    int64_t* out_idx, cudaStream_t st);
+
 // merge.cu
 int launch_init_state(const SearchState& s, int p_active, cudaStream_t st);
 int launch_merge_lists(const SearchState& s, int metric, int64_t idx_offset, float* out_scores, int64_t* out_idx,

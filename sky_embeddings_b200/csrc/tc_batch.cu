@@ -1,0 +1,500 @@
+// tc_batch.cu -- K2b: batched tcgen05 scorer for LARGE query batches (tensor-pipe bound regime).
+//
+// Same contraction forms as tc_search.cu (unweighted cosine / MSE, reference
+// utils/similarity.py:163-170, :188-192, :246-247), but shaped as a GEMM: an output tile is
+// 128 bank rows x 256 queries, both operands stream through a TMA ring (the query matrix no longer
+// fits in shared memory), fp32 accumulators live in two 256-column TMEM stages so that the epilogue
+// of one tile overlaps the MMAs of the next.  A bank tile is visited by all query groups back to
+// back, so it is read from HBM once and from L2 afterwards; the query matrix stays in L2.
+//
+// Top-k without a score matrix, for thousands of queries and k up to 4096: the bank is walked in
+// PHASES of geometrically growing size.  Inside a phase the kernel only filters: a score that
+// beats the query's current bound (the exact k-th best of everything scanned in earlier phases)
+// is appended to the CTA's candidate list.  Between phases a merge kernel folds the lists into the
+// running top-k ("carry") of every query and refreshes the bounds -- the running merge of
+// update_best_scores (utils/similarity.py:18-35), done once per phase instead of once per batch.
+// With doubling phases about k candidates per query survive per phase, so lists stay short; an
+// adversarially ordered bank is still exact: a list that fills up is pruned in place to its k best.
+#include <cstdlib>
+
+#include "bank.cuh"
+#include "ptx.cuh"
+#include "topk.cuh"
+
+namespace sky {
+
+constexpr int kTbBN = 256;                     // queries per tile (UMMA N)
+constexpr int kTbThreads = 6 * 32;             // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kTbEpiThreads = 128;
+constexpr int kTbStageA = kTileRows * 128;     // 16 KB: 128 rows x 64 bf16
+constexpr int kTbStageB = kTbBN * 128;         // 32 KB: 256 queries x 64 bf16
+constexpr int kTbStage = kTbStageA + kTbStageB;
+constexpr int kTbStages = 4;
+
+struct TbParams {
+    const float* rownorm;      // [rows_pad]
+    const float* qconst;       // [Qp] cosine |t|, MSE |t|^2
+    const float* bound1;       // [Qp] pre-filter coefficients (see batch_bounds_kernel)
+    const float* bound2;       // [Qp]
+    const uint64_t* tauc;      // [Qp] exact bound: composite of the current k-th best (0 = none)
+    uint64_t* lthr;            // [P][Qp] CTA-local bound after an overflow prune (0 = none)
+    uint64_t* lists;           // [P][Qp][cap]
+    int* counts;               // [P][Qp]
+    int Qp, nq, cap, k, groups, metric, kblocks;
+    int64_t rows;              // valid bank rows
+    int tile0, tile1;          // tiles [tile0, tile1) of this phase
+    float inv_dd;
+};
+
+__device__ __forceinline__ int ld_cg_i32(const int* p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg_i32(int* p, int v) { __stcg(p, v); }
+// barrier over `nthreads` threads that also ORs a predicate
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %3, 0;\n\t"
+        "bar.red.or.pred p, %1, %2, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r) : "r"(id), "r"(nthreads), "r"(static_cast<uint32_t>(pred)) : "memory");
+    return r != 0;
+}
+
+template <int kUnused>
+__global__ void __launch_bounds__(kTbThreads, 1)
+tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TbParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sStage = base;                                                   // [stages][A 16 KB | B 32 KB]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + kTbStages * kTbStage);   // [stages]
+    uint64_t* empty_bar = full_bar + kTbStages;
+    uint64_t* tmem_full = empty_bar + kTbStages;                                    // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                                           // [2]
+    unsigned long long* sTau = reinterpret_cast<unsigned long long*>(tmem_empty + 2);   // [2][256] exact bound (composite)
+    float* sB1 = reinterpret_cast<float*>(sTau + 2 * kTbBN);                        // [2][256] pre-filter coefficients
+    float* sB2 = sB1 + 2 * kTbBN;                                                   // [2][256]
+    float* sQc = sB2 + 2 * kTbBN;                                                   // [2][256] |t| or |t|^2
+    int* sCnt = reinterpret_cast<int*>(sQc + 2 * kTbBN);                            // [2][256] list fill of this CTA
+    uint32_t* sHist = reinterpret_cast<uint32_t*>(sCnt + 2 * kTbBN);                // [4][256]
+    uint32_t* sTmemBase = sHist + 4 * 256;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool largest = (p.metric == SKY_COSINE);
+    const int KB = p.kblocks, G = p.groups;
+    const int ntiles = p.tile1 - p.tile0;
+    const int my_tiles = (ntiles > static_cast<int>(blockIdx.x))
+                             ? (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+    const int visits = my_tiles * G;
+    auto tile_of = [&](int it) -> int { return p.tile0 + static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x); };
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < kTbStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(sTmemBase, 2 * kTbBN);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *sTmemBase;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int v = 0; v < visits; ++v) {
+                const int tile = tile_of(v / G), g = v % G;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, 32);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kTbStage);
+                    unsigned char* dst = sStage + static_cast<size_t>(stage) * kTbStage;
+                    // bank: tile-major, (tile, k-block) = 128 consecutive rows of a [rows_pad * KB, 64] tensor
+                    ptx::tma_load_2d(&tmap_a, dst, &full_bar[stage], 0, (tile * KB + kb) * kTileRows, 0x1000000000000000ull);
+                    ptx::tma_load_2d(&tmap_b, dst + kTbStageA, &full_bar[stage], kb * kKBlock, g * kTbBN, ptx::kEvictLast);
+                    if (++stage == kTbStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileRows, kTbBN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int v = 0; v < visits; ++v) {
+                const int acc = v & 1;
+                const uint32_t acc_phase = (v >> 1) & 1;
+                ptx::mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1, 32);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kTbBN);
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(sStage + static_cast<size_t>(stage) * kTbStage);
+                    const uint32_t b_addr = a_addr + kTbStageA;
+#pragma unroll
+                    for (int k = 0; k < kKBlock / 16; ++k) {
+                        const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_addr + k * 32);
+                        const uint64_t b_desc = ptx::make_sw128_kmajor_desc(b_addr + k * 32);
+                        ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == kTbStages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue: 4 warps, warp & 3 = TMEM lane quarter =====================
+        const int e = warp - 2;                   // 0..3: histogram slot, prune ownership
+        const int quarter = warp & 3;
+        const int et = tid - 64;                  // 0..127
+        const uint32_t hist = smem_addr(sHist + e * 256);
+        uint64_t* my_lists = p.lists + static_cast<size_t>(blockIdx.x) * p.Qp * p.cap;
+        int* my_counts = p.counts + static_cast<size_t>(blockIdx.x) * p.Qp;
+        uint64_t* my_lthr = p.lthr + static_cast<size_t>(blockIdx.x) * p.Qp;
+
+        // per-query state of a visit's query group is staged in shared memory: pre-filter coefficients, |t|,
+        // the exact bound max(global k-th best, CTA-local bound) and the fill of this CTA's list.  It is
+        // prefetched into registers one visit ahead (thread et owns queries et and et + 128 of the group).
+        float nb1[2], nb2[2], nqc[2];
+        unsigned long long ntau[2];
+        int ncnt[2];
+        auto prefetch_group = [&](int gq) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int q = gq * kTbBN + et + j * 128;
+                nb1[j] = __ldg(p.bound1 + q); nb2[j] = __ldg(p.bound2 + q); nqc[j] = __ldg(p.qconst + q);
+                const unsigned long long tg = __ldg(reinterpret_cast<const unsigned long long*>(p.tauc + q));
+                const unsigned long long tl = ld_cg_u64(my_lthr + q);
+                ntau[j] = tl > tg ? tl : tg;
+                ncnt[j] = ld_cg_i32(my_counts + q);
+            }
+        };
+        prefetch_group(0);
+
+        for (int v = 0; v < visits; ++v) {
+            const int it = v / G, g = v - it * G;
+            const int tile = tile_of(it);
+            const int acc = v & 1;
+            const uint32_t acc_phase = (v >> 1) & 1;
+            const int buf = v & 1;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int i = buf * kTbBN + et + j * 128;
+                sB1[i] = nb1[j]; sB2[i] = nb2[j]; sQc[i] = nqc[j]; sTau[i] = ntau[j]; sCnt[i] = ncnt[j];
+            }
+            // the next group is a different set of queries, except when there is a single group: then its
+            // counts are re-read after this visit's write-back (see the end of the loop)
+            if (G > 1) prefetch_group((g + 1 == G) ? 0 : g + 1);
+            const int64_t row = static_cast<int64_t>(tile) * kTileRows + quarter * 32 + lane;
+            const bool valid = row < p.rows;
+            const float rn = valid ? __ldg(p.rownorm + row) : 0.f;
+            const float mx = sqrtf(rn);
+            // per-row term of the pre-filter (see batch_bounds_kernel): cosine bound = b1*|z| + b2, MSE bound = b1 + rn/2 (lowered)
+            const float rterm = largest ? mx : 0.5f * rn * (1.0f - 4e-6f);
+            ptx::named_bar_sync(1, kTbEpiThreads);           // bounds of this visit are in shared memory
+            if (lane == 0) ptx::mbar_wait_relaxed(&tmem_full[acc], acc_phase, 64);
+            __syncwarp();
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTbBN);
+            const uint32_t b1_addr = smem_addr(sB1 + buf * kTbBN), b2_addr = smem_addr(sB2 + buf * kTbBN);
+            bool inserted = false;
+#pragma unroll 1
+            for (int c = 0; c < kTbBN / 32; ++c) {
+                uint32_t vv[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c * 32, vv);
+                ptx::tmem_ld_wait();
+                if (c == kTbBN / 32 - 1) {                   // accumulator fully in registers: hand it back
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+                }
+                uint32_t mbits = 0;
+#pragma unroll
+                for (int gq = 0; gq < 8; ++gq) {
+                    float b1[4], b2[4];
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(b1[0]), "=f"(b1[1]), "=f"(b1[2]), "=f"(b1[3]) : "r"(b1_addr + (c * 32 + gq * 4) * 4));
+                    if (largest)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(b2[0]), "=f"(b2[1]), "=f"(b2[2]), "=f"(b2[3]) : "r"(b2_addr + (c * 32 + gq * 4) * 4));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float dot = __uint_as_float(vv[gq * 4 + u]);
+                        const float bound = largest ? fmaf(b1[u], rterm, b2[u]) : b1[u] + rterm;
+                        mbits |= (!(dot < bound) ? 1u : 0u) << (gq * 4 + u);       // NaN passes
+                    }
+                }
+                mbits = valid ? mbits : 0u;
+                // columns beyond the real queries carry a +inf bound and never pass
+                uint32_t cols = __reduce_or_sync(0xffffffffu, mbits);
+#pragma unroll 1
+                while (cols) {
+                    const int j = __ffs(cols) - 1;
+                    cols &= cols - 1;
+                    const int q = g * kTbBN + c * 32 + j;
+                    const int qi = buf * kTbBN + c * 32 + j;
+                    bool pass = (mbits >> j) & 1u;
+                    uint64_t comp = 0;
+                    if (pass) {
+                        float dot = 0.f;
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) dot = (jj == j) ? __uint_as_float(vv[jj]) : dot;
+                        const float qcv = sQc[qi];
+                        const float sv = largest ? dot / fmaf(qcv, mx, 1e-6f) : (qcv - 2.0f * dot + rn) * p.inv_dd;
+                        comp = make_composite(score_to_key(sv, largest), static_cast<uint32_t>(row));
+                        pass = comp > sTau[qi];
+                    }
+                    const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+                    if (pm) {
+                        int basepos = 0;
+                        const int leader = __ffs(pm) - 1;
+                        if (lane == leader) basepos = static_cast<int>(atoms_add_u32(smem_addr(&sCnt[qi]), static_cast<uint32_t>(__popc(pm))));
+                        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+                        // cap >= k + 256 and at most 128 rows per visit: the list cannot overflow before the check below
+                        if (pass) st_cg_u64(my_lists + static_cast<size_t>(q) * p.cap + basepos + __popc(pm & ((1u << lane) - 1u)), comp);
+                        inserted = true;
+                    }
+                }
+            }
+            // write the fills back; lists of this group that could not take another 128 rows are pruned in place
+            // to their k best (rare once bounds exist), which also yields a CTA-local bound
+            if (named_bar_or(3, kTbEpiThreads, inserted)) {
+                for (int qq = e; qq < kTbBN; qq += 4) {
+                    const int q = g * kTbBN + qq;
+                    int n = sCnt[buf * kTbBN + qq];
+                    if (n > p.cap - kTileRows) {
+                        uint64_t* lst = my_lists + static_cast<size_t>(q) * p.cap;
+                        const uint64_t kth = warp_select_kth(lst, n, p.k, hist);
+                        n = warp_compact_ge(lst, n, kth);
+                        if (lane == 0) st_cg_u64(my_lthr + q, kth);
+                        __syncwarp();
+                    }
+                    if (lane == 0) st_cg_i32(my_counts + q, n);
+                }
+                ptx::named_bar_sync(2, kTbEpiThreads);
+            }
+            if (G == 1) prefetch_group(0);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 2 * kTbBN);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// between phases
+// ---------------------------------------------------------------------------------------------
+// Pre-filter coefficients of every query from its exact bound tauc (composite of the k-th best so far):
+//   cosine:  s = dot / (qc |z| + 1e-6) >= tau   <=>  dot >= tau qc |z| + tau 1e-6      -> b1 = tau qc, b2 = tau 1e-6
+//   MSE:     s = (qc - 2 dot + rn) / D^2 <= tau <=>  dot >= (qc - tau D^2) / 2 + rn/2  -> b1 = (qc - tau D^2) / 2
+// both moved a few 1e-6 relative towards "pass" so that fp32 rounding can never reject what the exact
+// composite test would accept.  No bound yet: everything passes.  Padding queries: nothing passes.
+__global__ void batch_bounds_kernel(const uint64_t* __restrict__ tauc, const float* __restrict__ qconst, int nq, int Qp,
+                                    int metric, float dd, float* __restrict__ b1, float* __restrict__ b2) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Qp) return;
+    const bool largest = metric == SKY_COSINE;
+    float o1, o2;
+    if (q >= nq) { o1 = largest ? 0.f : INFINITY; o2 = INFINITY; }
+    else if (tauc[q] == 0ull) { o1 = largest ? 0.f : -INFINITY; o2 = -INFINITY; }
+    else {
+        const float tau = key_to_score(composite_key(tauc[q]), largest);
+        const float qc = qconst[q];
+        if (largest) {
+            const float f = tau >= 0.f ? (1.0f - 4e-6f) : (1.0f + 4e-6f);
+            o1 = tau * qc * f;
+            o2 = tau * 1e-6f * f;
+        } else {
+            const float td = tau * dd;
+            o1 = 0.5f * (qc - td) - 2e-6f * (fabsf(qc) + fabsf(td));
+            o2 = 0.f;
+        }
+    }
+    b1[q] = o1;
+    b2[q] = o2;
+}
+
+// carry[q][kpad] (running top-k as composites, 0 = empty) + the P lists of this phase -> new carry, tauc;
+// resets the lists.  last != 0: also writes the final (score, index) rows.
+constexpr int kMpThreads = 256;
+__global__ void __launch_bounds__(kMpThreads)
+merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, const uint64_t* __restrict__ lists,
+                   int* __restrict__ counts, uint64_t* __restrict__ lthr, int P, int Qp, int cap, int k, int kpad, int kMpPool, int largest,
+                   int last, int nq, int64_t idx_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
+    uint64_t* pool = sel + kpad;                              // [kMpPool]
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t scratch[4];
+    __shared__ uint32_t npool;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kMpThreads / 32;
+    if (tid == 0) npool = 0;
+    __syncthreads();
+    uint64_t* cq = carry + static_cast<size_t>(q) * kpad;
+    const uint64_t keep_gt = tauc[q];      // list entries were admitted with comp > tauc: all of them count
+    (void)keep_gt;
+    for (int j = tid; j < k; j += kMpThreads) {
+        const uint64_t v = cq[j];
+        if (v) { const uint32_t pos = atomicAdd(&npool, 1u); if (pos < kMpPool) pool[pos] = v; }
+    }
+    for (int p = warp; p < P; p += nwarps) {
+        const int n = counts[static_cast<size_t>(p) * Qp + q];
+        const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t pos = atomicAdd(&npool, 1u);
+            if (pos < kMpPool) pool[pos] = e[i];
+        }
+    }
+    __syncthreads();
+    const int np = static_cast<int>(npool);
+    if (np <= kMpPool) {
+        block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch);
+    } else {
+        // first phase / adversarial order: more candidates than the pool holds -> select straight from L2
+        auto fetch = [&](int j) -> uint64_t {
+            if (j < k) return cq[j];
+            const int jj = j - k;
+            const int p = jj / cap, i = jj - p * cap;
+            if (i >= counts[static_cast<size_t>(p) * Qp + q]) return 0ull;
+            return lists[(static_cast<size_t>(p) * Qp + q) * cap + i];
+        };
+        block_select_sort(fetch, k + P * cap, k, kpad, sel, hist, scratch);
+    }
+    __syncthreads();
+    for (int j = tid; j < kpad; j += kMpThreads) cq[j] = (j < k) ? sel[j] : 0ull;
+    if (tid == 0) tauc[q] = sel[k - 1];        // 0 while fewer than k rows have been seen
+    for (int p = tid; p < P; p += kMpThreads) { counts[static_cast<size_t>(p) * Qp + q] = 0; lthr[static_cast<size_t>(p) * Qp + q] = 0ull; }
+    if (last && q < nq) {
+        for (int j = tid; j < k; j += kMpThreads) {
+            const uint64_t c = sel[j];
+            float* so = out_scores + static_cast<size_t>(q) * k + j;
+            int64_t* io = out_idx + static_cast<size_t>(q) * k + j;
+            if (c == 0) { *so = largest ? -INFINITY : INFINITY; *io = -1; }
+            else { *so = key_to_score(composite_key(c), largest != 0); *io = static_cast<int64_t>(composite_idx(c)) + idx_offset; }
+        }
+    }
+}
+
+__global__ void batch_init_kernel(uint64_t* carry, uint64_t* tauc, int* counts, uint64_t* lthr, size_t n_carry, size_t n_q, size_t n_pq) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n_carry) carry[i] = 0ull;
+    if (i < n_q) tauc[i] = 0ull;
+    if (i < n_pq) { counts[i] = 0; lthr[i] = 0ull; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows);                 // tc_search.cu
+int launch_pack_queries(const float* t, int Q, int D, int Dp, int q_pad, int metric, void* bq, float* qconst, cudaStream_t st);
+
+static int tb_next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+
+bool tc_batch_supported(const sky_bank* b, int metric, bool weighted, int n_top, int k) {
+    return b->dtype == SKY_BF16 && b->L == 1 && !weighted && n_top == 0 && (metric == SKY_COSINE || metric == SKY_MSE) &&
+           b->rows > 0 && k <= 4096 && b->tmap_ready;
+}
+
+int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64_t idx_offset, float* out_scores,
+                    int64_t* out_idx, cudaStream_t st) {
+    const int Qp = static_cast<int>(round_up(Q, kTbBN));
+    const int G = Qp / kTbBN;
+    const int KB = b->Dp / kKBlock;
+    const int num_tiles = static_cast<int>((b->rows + kTileRows - 1) / kTileRows);
+    const int P = num_tiles < b->num_sms ? num_tiles : b->num_sms;
+    const int kpad = tb_next_pow2(k);
+    const int cap = k + 2 * kTileRows;
+    // workspace: lists | carry | tauc | lthr | counts | b1 | b2 | qconst | bq
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += static_cast<size_t>(round_up(static_cast<int64_t>(bytes), 256)); return o; };
+    const size_t o_lists = take(static_cast<size_t>(P) * Qp * cap * 8);
+    const size_t o_carry = take(static_cast<size_t>(Qp) * kpad * 8);
+    const size_t o_tauc = take(static_cast<size_t>(Qp) * 8);
+    const size_t o_lthr = take(static_cast<size_t>(P) * Qp * 8);
+    const size_t o_counts = take(static_cast<size_t>(P) * Qp * 4);
+    const size_t o_b1 = take(static_cast<size_t>(Qp) * 4);
+    const size_t o_b2 = take(static_cast<size_t>(Qp) * 4);
+    const size_t o_qc = take(static_cast<size_t>(Qp) * 4);
+    const size_t o_bq = take(static_cast<size_t>(Qp) * b->Dp * 2);
+    int rc = ensure_ws(b, off);
+    if (rc) return rc;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(b->ws);
+    uint64_t* lists = reinterpret_cast<uint64_t*>(ws + o_lists);
+    uint64_t* carry = reinterpret_cast<uint64_t*>(ws + o_carry);
+    uint64_t* tauc = reinterpret_cast<uint64_t*>(ws + o_tauc);
+    uint64_t* lthr = reinterpret_cast<uint64_t*>(ws + o_lthr);
+    int* counts = reinterpret_cast<int*>(ws + o_counts);
+    float* b1 = reinterpret_cast<float*>(ws + o_b1);
+    float* b2 = reinterpret_cast<float*>(ws + o_b2);
+    float* qconst = reinterpret_cast<float*>(ws + o_qc);
+    void* bq = ws + o_bq;
+
+    rc = launch_pack_queries(t, Q, b->D, b->Dp, Qp, metric, bq, qconst, st);
+    if (rc) return rc;
+    {
+        const size_t n = static_cast<size_t>(P) * Qp > static_cast<size_t>(Qp) * kpad ? static_cast<size_t>(P) * Qp : static_cast<size_t>(Qp) * kpad;
+        batch_init_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(carry, tauc, counts, lthr, static_cast<size_t>(Qp) * kpad,
+                                                                               static_cast<size_t>(Qp), static_cast<size_t>(P) * Qp);
+        SKY_LAUNCH_CHECK("batch_init_kernel");
+    }
+    CUtensorMap tmq;
+    rc = make_tmap_2d(&tmq, bq, Qp, b->Dp, kTbBN);
+    if (rc) return rc;
+
+    const size_t smem = 1024 + static_cast<size_t>(kTbStages) * kTbStage + (2 * kTbStages + 4) * 8 + 2 * kTbBN * 8 + 8 * kTbBN * 4 + 4 * 256 * 4 + 64;
+    SKY_CUDA(cudaFuncSetAttribute(tc_batch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SKY_CUDA(cudaFuncSetAttribute(merge_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+
+    TbParams p;
+    p.rownorm = b->rownorm; p.qconst = qconst; p.bound1 = b1; p.bound2 = b2; p.tauc = tauc; p.lthr = lthr;
+    p.lists = lists; p.counts = counts;
+    p.Qp = Qp; p.nq = Q; p.cap = cap; p.k = k; p.groups = G; p.metric = metric; p.kblocks = KB;
+    p.rows = b->rows;
+    p.inv_dd = 1.0f / (static_cast<float>(b->D) * static_cast<float>(b->D));
+    const float dd = static_cast<float>(b->D) * static_cast<float>(b->D);
+
+    // phases: 1, 1, 2, 4, ... tiles per CTA
+    int t0 = 0;
+    int per_cta = 1;
+    bool first = true;
+    { static const char* e = getenv("SKY_TB_PHASE0"); if (e && atoi(e) >= 1) per_cta = atoi(e); }
+    while (t0 < num_tiles) {
+        int t1 = t0 + per_cta * P;
+        if (t1 > num_tiles || num_tiles - t1 < P) t1 = num_tiles;      // fold a short tail into this phase
+        batch_bounds_kernel<<<(Qp + 255) / 256, 256, 0, st>>>(tauc, qconst, Q, Qp, metric, dd, b1, b2);
+        SKY_LAUNCH_CHECK("batch_bounds_kernel");
+        p.tile0 = t0; p.tile1 = t1;
+        const int grid = (t1 - t0) < P ? (t1 - t0) : P;
+        prof_mark(b, st);
+        tc_batch_kernel<0><<<grid, kTbThreads, smem, st>>>(b->tmap_bank, tmq, p);
+        prof_mark(b, st);
+        SKY_LAUNCH_CHECK("tc_batch_kernel");
+        const int last = t1 == num_tiles ? 1 : 0;
+        // candidate pool in shared memory: the first phase admits every row (128 per CTA per query), later ones few
+        int pool = first ? (grid * kTileRows + k) : 4096;
+        if (static_cast<size_t>(kpad + pool) * 8 > 196 * 1024) pool = (196 * 1024) / 8 - kpad;
+        const size_t msmem = static_cast<size_t>(kpad + pool) * 8;
+        merge_phase_kernel<<<Qp, kMpThreads, msmem, st>>>(carry, tauc, lists, counts, lthr, P, Qp, cap, k, kpad, pool,
+                                                         metric_largest(metric) ? 1 : 0, last, Q, idx_offset, out_scores, out_idx);
+        SKY_LAUNCH_CHECK("merge_phase_kernel");
+        t0 = t1;
+        if (!first) per_cta *= 2;
+        first = false;
+    }
+    return SKY_OK;
+}
+
+}  // namespace sky

@@ -446,7 +446,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 [rows, Dp] tensor (row pitch Dp elements), box = 64 columns x box_rows rows, 128-byte swizzle.
-static int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows) {
+int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_error(SKY_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(Dp), static_cast<cuuint64_t>(rows)};
@@ -457,6 +457,12 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, i
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(SKY_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
+    return SKY_OK;
+}
+
+int launch_pack_queries(const float* t, int Q, int D, int Dp, int q_pad, int metric, void* bq, float* qconst, cudaStream_t st) {
+    pack_queries_kernel<<<q_pad, 256, 0, st>>>(t, Q, D, Dp, q_pad, metric, reinterpret_cast<__nv_bfloat16*>(bq), qconst);
+    SKY_LAUNCH_CHECK("pack_queries_kernel");
     return SKY_OK;
 }
 

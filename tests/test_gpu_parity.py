@@ -524,3 +524,63 @@ def test_pixel_odd_row_length_and_subrange(dev):
         from sky_embeddings_b200 import _lib as LL
         LL.check(bank.lib.sky_bank_finalize(None, None))
     bank.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# batched tensor path (K2b): GEMM-shaped kernel with phased bounds, large query batches
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["cosine", "MSE"])
+@pytest.mark.parametrize("n,Q,k,D", [(60000, 300, 100, 768), (777, 257, 10, 768), (130, 512, 100, 64),
+                                     (40000, 260, 1000, 128), (19000, 1, 5, 768)])
+def test_batch_path_vs_oracle(dev, metric, n, Q, k, D):
+    from sky_embeddings_b200 import Bank, synth
+    lat = synth.latents(n, 1, D, stream=201)
+    bank = Bank.from_latents(torch.from_numpy(lat).to(dev), norm_rows=64, dtype="bf16")
+    z = bank.download().cpu().numpy()[:, 0]
+    rng = np.random.Generator(np.random.PCG64(17))
+    rows = rng.integers(0, n, Q)
+    t = (z[rows] + 0.3 * rng.standard_normal((Q, D))).astype(np.float32)
+    sc, ix = bank.search(torch.from_numpy(t).to(dev), None, k=k, metric=metric, path="batch")
+    sc, ix = sc.cpu().numpy(), ix.cpu().numpy()
+    model = _exact_model_scores(z, t, metric)          # what the contraction computes (bf16 queries), fp64
+    kk = min(k, n)
+    for q in range(Q):
+        ms, mi = O.topk(model[q], k, metric)
+        ok, msg = O.check_topk_parity(sc[q], ix[q], ms, mi, 2e-5, all_scores=model[q])
+        assert ok, f"batch-vs-model n={n} q{q}: {msg}"
+        if n < k:
+            assert np.all(ix[q, kk:] == -1)
+    # and against the oracle on the stored bank at the bf16 tolerance, for a few queries
+    for q in range(0, Q, max(1, Q // 5)):
+        all_ref = O.item_scores(t[q].astype(np.float64), np.ones(D), z[:, None].astype(np.float64), metric, "min")
+        ref_s, ref_i = O.topk(all_ref, k, metric)
+        ok, msg = O.check_topk_parity(sc[q], ix[q], ref_s, ref_i, REL_BF16, all_scores=all_ref)
+        assert ok, f"batch-vs-oracle q{q}: {msg}"
+    bank.close()
+
+
+def test_batch_path_adversarial_order_and_nan(dev):
+    """Scores improve with the row index, so every row beats every bound of the earlier phases (lists
+    overflow and are pruned in place); plus NaN rows, which rank first for cosine and last for MSE."""
+    from sky_embeddings_b200 import Bank
+    n, D, Q, k = 150000, 64, 130, 100
+    rng = np.random.Generator(np.random.PCG64(23))
+    t0 = rng.standard_normal(D).astype(np.float32)
+    e = rng.standard_normal(D).astype(np.float32)
+    scale = (1.0 + np.arange(n, 0, -1, dtype=np.float32) / 4096.0)[:, None]
+    lat = (t0[None, :] + scale * e[None, :]).astype(np.float32)
+    lat[[11, 70000]] = np.nan
+    bank = Bank.from_latents(torch.from_numpy(lat[:, None, :]).to(dev), norm_rows=None, dtype="bf16")
+    z = bank.download().cpu().numpy()[:, 0]
+    t = (t0[None, :] + 0.01 * rng.standard_normal((Q, D))).astype(np.float32)
+    for metric in ("MSE", "cosine"):
+        sc, ix = bank.search(torch.from_numpy(t).to(dev), None, k=k, metric=metric, path="batch")
+        sc, ix = sc.cpu().numpy(), ix.cpu().numpy()
+        model = _exact_model_scores(z, t, metric)
+        for q in range(0, Q, 7):
+            ms, mi = O.topk(model[q], k, metric)
+            ok, msg = O.check_topk_parity(sc[q], ix[q], ms, mi, 2e-5, all_scores=model[q])
+            assert ok, f"{metric} q{q}: {msg}"
+        if metric == "cosine":
+            assert set(ix[0, :2].tolist()) == {11, 70000} and np.isnan(sc[0, :2]).all()
+    bank.close()
