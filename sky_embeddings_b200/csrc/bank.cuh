@@ -108,6 +108,7 @@ int debug_read_trace(unsigned long long* h_out, int n);
 int debug_read_epi(unsigned long long* h_out);
 
 // tc_batch.cu
+int debug_read_tb_trace(long long* h_out, int n);
 bool tc_batch_supported(const sky_bank* b, int metric, bool weighted, int n_top, int k);
 int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64_t idx_offset, float* out_scores,
                     int64_t* out_idx, cudaStream_t st);

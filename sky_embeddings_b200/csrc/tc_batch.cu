@@ -43,6 +43,7 @@ struct TbParams {
     int Qp, nq, cap, k, groups, metric, kblocks;
     int64_t rows;              // valid bank rows
     int tile0, tile1;          // tiles [tile0, tile1) of this phase
+    int debug;                 // experiments: bit0 epilogue only drains TMEM, bit1 no MMA issue
     float inv_dd;
 };
 
@@ -60,7 +61,24 @@ __device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
     return r != 0;
 }
 
-template <int kUnused>
+// debug timeline (SKY_TB_DEBUG bit 5 = 32): clock64 stamps of CTA 0, epilogue warp e = 0, per visit of the launch:
+// [0] visit start, [1] accumulator ready, [2] chunks done, [3] write-back done, [4] = 1 if anything was inserted
+constexpr int kTbTrace = 4096;
+__device__ long long g_tb_trace[kTbTrace * 4 * 5];
+#define TB_TRACE(slot, val) do { if ((p.debug & 32) && blockIdx.x == 0 && lane == 0 && v < kTbTrace) g_tb_trace[(v * 4 + e) * 5 + (slot)] = (val); } while (0)
+
+// tcgen05.wait::ld that also "touches" the destination registers of an earlier tcgen05.ld, so that the compiler
+// cannot move their first use above the wait when other work sits between the load and the wait
+__device__ __forceinline__ void tmem_ld_wait_touch(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+
+template <bool COS>
 __global__ void __launch_bounds__(kTbThreads, 1)
 tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TbParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -79,7 +97,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t* sTmemBase = sHist + 4 * 256;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool largest = (p.metric == SKY_COSINE);
+    constexpr bool largest = COS;
     const int KB = p.kblocks, G = p.groups;
     const int ntiles = p.tile1 - p.tile0;
     const int my_tiles = (ntiles > static_cast<int>(blockIdx.x))
@@ -142,7 +160,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     for (int k = 0; k < kKBlock / 16; ++k) {
                         const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_addr + k * 32);
                         const uint64_t b_desc = ptx::make_sw128_kmajor_desc(b_addr + k * 32);
-                        ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(p.debug & 2)) ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == kTbStages) { stage = 0; phase ^= 1; }
@@ -193,6 +211,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             // the next group is a different set of queries, except when there is a single group: then its
             // counts are re-read after this visit's write-back (see the end of the loop)
             if (G > 1) prefetch_group((g + 1 == G) ? 0 : g + 1);
+            TB_TRACE(0, clock64());
             const int64_t row = static_cast<int64_t>(tile) * kTileRows + quarter * 32 + lane;
             const bool valid = row < p.rows;
             const float rn = valid ? __ldg(p.rownorm + row) : 0.f;
@@ -202,36 +221,31 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             ptx::named_bar_sync(1, kTbEpiThreads);           // bounds of this visit are in shared memory
             if (lane == 0) ptx::mbar_wait_relaxed(&tmem_full[acc], acc_phase, 64);
             __syncwarp();
+            TB_TRACE(1, clock64());
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTbBN);
-            const uint32_t b1_addr = smem_addr(sB1 + buf * kTbBN), b2_addr = smem_addr(sB2 + buf * kTbBN);
             bool inserted = false;
-#pragma unroll 1
-            for (int c = 0; c < kTbBN / 32; ++c) {
-                uint32_t vv[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c * 32, vv);
-                ptx::tmem_ld_wait();
-                if (c == kTbBN / 32 - 1) {                   // accumulator fully in registers: hand it back
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-                }
+            // one 32-column chunk: conservative pre-filter in the space of the accumulator (one FMA / ADD and one
+            // compare per score, coefficients read with 128-bit shared loads issued up front), then the rare exact path
+            auto process = [&](const uint32_t (&vv)[32], int c) {
+                const float4* pb1 = reinterpret_cast<const float4*>(sB1 + buf * kTbBN + c * 32);
+                const float4* pb2 = reinterpret_cast<const float4*>(sB2 + buf * kTbBN + c * 32);
+                float4 c1[8], c2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { c1[i] = pb1[i]; if (COS) c2[i] = pb2[i]; }
                 uint32_t mbits = 0;
 #pragma unroll
-                for (int gq = 0; gq < 8; ++gq) {
-                    float b1[4], b2[4];
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(b1[0]), "=f"(b1[1]), "=f"(b1[2]), "=f"(b1[3]) : "r"(b1_addr + (c * 32 + gq * 4) * 4));
-                    if (largest)
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(b2[0]), "=f"(b2[1]), "=f"(b2[2]), "=f"(b2[3]) : "r"(b2_addr + (c * 32 + gq * 4) * 4));
+                for (int i = 0; i < 8; ++i) {
+                    const float b1[4] = {c1[i].x, c1[i].y, c1[i].z, c1[i].w};
+                    const float b2[4] = {COS ? c2[i].x : 0.f, COS ? c2[i].y : 0.f, COS ? c2[i].z : 0.f, COS ? c2[i].w : 0.f};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const float dot = __uint_as_float(vv[gq * 4 + u]);
-                        const float bound = largest ? fmaf(b1[u], rterm, b2[u]) : b1[u] + rterm;
-                        mbits |= (!(dot < bound) ? 1u : 0u) << (gq * 4 + u);       // NaN passes
+                        const float dot = __uint_as_float(vv[i * 4 + u]);
+                        const float bound = COS ? fmaf(b1[u], rterm, b2[u]) : b1[u] + rterm;
+                        mbits |= (!(dot < bound) ? 1u : 0u) << (i * 4 + u);       // NaN passes
                     }
                 }
+                if (p.debug & 4) mbits = 0;
                 mbits = valid ? mbits : 0u;
                 // columns beyond the real queries carry a +inf bound and never pass
                 uint32_t cols = __reduce_or_sync(0xffffffffu, mbits);
@@ -252,7 +266,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         comp = make_composite(score_to_key(sv, largest), static_cast<uint32_t>(row));
                         pass = comp > sTau[qi];
                     }
-                    const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+                    const uint32_t pm = (p.debug & 16) ? 0u : __ballot_sync(0xffffffffu, pass);
                     if (pm) {
                         int basepos = 0;
                         const int leader = __ffs(pm) - 1;
@@ -263,25 +277,53 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         inserted = true;
                     }
                 }
+            };
+            // software pipeline over the 8 chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c is filtered
+            uint32_t va[32], vb[32];
+            ptx::tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll 1
+            for (int c2 = 0; c2 < kTbBN / 64; ++c2) {
+                tmem_ld_wait_touch(va);
+                ptx::tmem_ld_32x32b_x32(taddr + (2 * c2 + 1) * 32, vb);
+                if (!(p.debug & 1)) process(va, 2 * c2);
+                tmem_ld_wait_touch(vb);
+                if (c2 + 1 < kTbBN / 64) {
+                    ptx::tmem_ld_32x32b_x32(taddr + (2 * c2 + 2) * 32, va);
+                } else {                                      // accumulator fully in registers: hand it back
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+                }
+                if (!(p.debug & 1)) process(vb, 2 * c2 + 1);
             }
+            TB_TRACE(2, clock64());
+            TB_TRACE(4, inserted ? 1 : 0);
             // write the fills back; lists of this group that could not take another 128 rows are pruned in place
             // to their k best (rare once bounds exist), which also yields a CTA-local bound
-            if (named_bar_or(3, kTbEpiThreads, inserted)) {
-                for (int qq = e; qq < kTbBN; qq += 4) {
-                    const int q = g * kTbBN + qq;
-                    int n = sCnt[buf * kTbBN + qq];
-                    if (n > p.cap - kTileRows) {
-                        uint64_t* lst = my_lists + static_cast<size_t>(q) * p.cap;
-                        const uint64_t kth = warp_select_kth(lst, n, p.k, hist);
-                        n = warp_compact_ge(lst, n, kth);
-                        if (lane == 0) st_cg_u64(my_lthr + q, kth);
+            if (!(p.debug & 8) && named_bar_or(3, kTbEpiThreads, inserted)) {
+                // warp e owns queries [64 e, 64 e + 64) of the group; lane handles two of them
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int qq = e * 64 + h * 32 + lane;
+                    const int n = sCnt[buf * kTbBN + qq];
+                    uint32_t full = __ballot_sync(0xffffffffu, n > p.cap - kTileRows);
+                    while (full) {                                  // rare: prune one list per iteration, whole warp
+                        const int l = __ffs(full) - 1;
+                        full &= full - 1;
+                        const int qf = e * 64 + h * 32 + l;
+                        const int nf = __shfl_sync(0xffffffffu, n, l);
+                        uint64_t* lst = my_lists + static_cast<size_t>(g * kTbBN + qf) * p.cap;
+                        const uint64_t kth = warp_select_kth(lst, nf, p.k, hist);
+                        const int m = warp_compact_ge(lst, nf, kth);
+                        if (lane == 0) { st_cg_u64(my_lthr + g * kTbBN + qf, kth); st_cg_i32(my_counts + g * kTbBN + qf, m); }
                         __syncwarp();
                     }
-                    if (lane == 0) st_cg_i32(my_counts + q, n);
+                    if (!(n > p.cap - kTileRows)) st_cg_i32(my_counts + g * kTbBN + qq, n);
                 }
                 ptx::named_bar_sync(2, kTbEpiThreads);
             }
             if (G == 1) prefetch_group(0);
+            TB_TRACE(3, clock64());
         }
     }
 
@@ -401,6 +443,13 @@ __global__ void batch_init_kernel(uint64_t* carry, uint64_t* tauc, int* counts, 
 int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows);                 // tc_search.cu
 int launch_pack_queries(const float* t, int Q, int D, int Dp, int q_pad, int metric, void* bq, float* qconst, cudaStream_t st);
 
+int debug_read_tb_trace(long long* h_out, int n) {
+    if (n > kTbTrace * 20) n = kTbTrace * 20;
+    SKY_CUDA(cudaDeviceSynchronize());
+    SKY_CUDA(cudaMemcpyFromSymbol(h_out, g_tb_trace, sizeof(long long) * n));
+    return SKY_OK;
+}
+
 static int tb_next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
 bool tc_batch_supported(const sky_bank* b, int metric, bool weighted, int n_top, int k) {
@@ -455,7 +504,8 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     if (rc) return rc;
 
     const size_t smem = 1024 + static_cast<size_t>(kTbStages) * kTbStage + (2 * kTbStages + 4) * 8 + 2 * kTbBN * 8 + 8 * kTbBN * 4 + 4 * 256 * 4 + 64;
-    SKY_CUDA(cudaFuncSetAttribute(tc_batch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SKY_CUDA(cudaFuncSetAttribute(tc_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SKY_CUDA(cudaFuncSetAttribute(tc_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SKY_CUDA(cudaFuncSetAttribute(merge_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
     TbParams p;
@@ -463,6 +513,7 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     p.lists = lists; p.counts = counts;
     p.Qp = Qp; p.nq = Q; p.cap = cap; p.k = k; p.groups = G; p.metric = metric; p.kblocks = KB;
     p.rows = b->rows;
+    { static const char* e = getenv("SKY_TB_DEBUG"); p.debug = e ? atoi(e) : 0; }
     p.inv_dd = 1.0f / (static_cast<float>(b->D) * static_cast<float>(b->D));
     const float dd = static_cast<float>(b->D) * static_cast<float>(b->D);
 
@@ -479,7 +530,8 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
         p.tile0 = t0; p.tile1 = t1;
         const int grid = (t1 - t0) < P ? (t1 - t0) : P;
         prof_mark(b, st);
-        tc_batch_kernel<0><<<grid, kTbThreads, smem, st>>>(b->tmap_bank, tmq, p);
+        if (metric == SKY_COSINE) tc_batch_kernel<true><<<grid, kTbThreads, smem, st>>>(b->tmap_bank, tmq, p);
+        else tc_batch_kernel<false><<<grid, kTbThreads, smem, st>>>(b->tmap_bank, tmq, p);
         prof_mark(b, st);
         SKY_LAUNCH_CHECK("tc_batch_kernel");
         const int last = t1 == num_tiles ? 1 : 0;
