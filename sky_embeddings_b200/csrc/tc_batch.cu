@@ -371,6 +371,7 @@ __global__ void batch_bounds_kernel(const uint64_t* __restrict__ tauc, const flo
 // carry[q][kpad] (running top-k as composites, 0 = empty) + the P lists of this phase -> new carry, tauc;
 // resets the lists.  last != 0: also writes the final (score, index) rows.
 constexpr int kMpThreads = 256;
+constexpr int kMpSample = 4096;
 __global__ void __launch_bounds__(kMpThreads)
 merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, const uint64_t* __restrict__ lists,
                    int* __restrict__ counts, uint64_t* __restrict__ lthr, int P, int Qp, int cap, int k, int kpad, int kMpPool, int largest,
@@ -378,6 +379,7 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
     uint64_t* pool = sel + kpad;                              // [kMpPool]
+    uint64_t* extra = (kMpPool > 2 * kMpSample) ? pool + kMpPool : nullptr;   // [kMpSample] survivors of the sampled pre-select
     __shared__ uint32_t hist[256];
     __shared__ uint32_t scratch[4];
     __shared__ uint32_t npool;
@@ -392,20 +394,58 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
         const uint64_t v = cq[j];
         if (v) { const uint32_t pos = atomicAdd(&npool, 1u); if (pos < kMpPool) pool[pos] = v; }
     }
-    for (int p = warp; p < P; p += nwarps) {
-        const int n = counts[static_cast<size_t>(p) * Qp + q];
-        const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
-        for (int i = lane; i < n; i += 32) {
-            const uint32_t pos = atomicAdd(&npool, 1u);
-            if (pos < kMpPool) pool[pos] = e[i];
+    // all list fills first (one L2 round trip instead of one per list), an exclusive scan gives every list its
+    // place in the pool, then the gather runs with independent loads (no atomics on the way)
+    __shared__ int s_n[1024];
+    __shared__ int s_off[1024];
+    for (int p = tid; p < P; p += kMpThreads) s_n[p] = counts[static_cast<size_t>(p) * Qp + q];
+    __syncthreads();
+    if (warp == 0) {
+        int run = static_cast<int>(npool);           // carry entries already in the pool
+        for (int p0 = 0; p0 < P; p0 += 32) {
+            const int n = (p0 + lane < P) ? s_n[p0 + lane] : 0;
+            int incl = n;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+            if (p0 + lane < P) s_off[p0 + lane] = run + incl - n;
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
+        if (lane == 0) npool = static_cast<uint32_t>(run);
+    }
+    __syncthreads();
+    for (int p = warp; p < P; p += nwarps) {
+        const int n = s_n[p], o = s_off[p];
+        const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
+        for (int i = lane; i < n; i += 32)
+            if (o + i < kMpPool) pool[o + i] = e[i];
     }
     __syncthreads();
     const int np = static_cast<int>(npool);
     if (np <= kMpPool) {
-        block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch);
+        bool done = false;
+        if (np > 2 * kMpSample && extra != nullptr) {
+            // big pool (first phase: every row of every CTA): select on a sample first -- its k-th best is a lower
+            // bound of the real one -- then keep only what beats it and finish on the few survivors
+            block_select_sort([&](int j) { return pool[j]; }, kMpSample, k, kpad, sel, hist, scratch);
+            __syncthreads();
+            const uint64_t tau0 = sel[k - 1];
+            __shared__ uint32_t nkeep;
+            if (tid == 0) nkeep = 0;
+            __syncthreads();
+            for (int j = tid; j < np; j += kMpThreads) {
+                const uint64_t v = pool[j];
+                if (v >= tau0 && v != 0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < kMpSample) extra[pos] = v; }
+            }
+            __syncthreads();
+            if (tau0 != 0 && nkeep <= kMpSample) {
+                block_select_sort([&](int j) { return extra[j]; }, static_cast<int>(nkeep), k, kpad, sel, hist, scratch);
+                done = true;
+            }
+            __syncthreads();
+        }
+        if (!done) block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch);
     } else {
-        // first phase / adversarial order: more candidates than the pool holds -> select straight from L2
+        // adversarial order / huge k: more candidates than the pool holds -> select straight from L2
         auto fetch = [&](int j) -> uint64_t {
             if (j < k) return cq[j];
             const int jj = j - k;
@@ -537,8 +577,9 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
         const int last = t1 == num_tiles ? 1 : 0;
         // candidate pool in shared memory: the first phase admits every row (128 per CTA per query), later ones few
         int pool = first ? (grid * kTileRows + k) : 4096;
-        if (static_cast<size_t>(kpad + pool) * 8 > 196 * 1024) pool = (196 * 1024) / 8 - kpad;
-        const size_t msmem = static_cast<size_t>(kpad + pool) * 8;
+        const int extra = pool > 2 * kMpSample ? kMpSample : 0;
+        if (static_cast<size_t>(kpad + pool + extra) * 8 > 196 * 1024) pool = (196 * 1024) / 8 - kpad - extra;
+        const size_t msmem = static_cast<size_t>(kpad + pool + extra) * 8;
         merge_phase_kernel<<<Qp, kMpThreads, msmem, st>>>(carry, tauc, lists, counts, lthr, P, Qp, cap, k, kpad, pool,
                                                          metric_largest(metric) ? 1 : 0, last, Q, idx_offset, out_scores, out_idx);
         SKY_LAUNCH_CHECK("merge_phase_kernel");
