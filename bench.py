@@ -44,7 +44,11 @@ WORKLOADS = {
     "c3s": (1_000_000, 768, 4096, 100, "MSE"),
     # BASELINE configs[3] ("C4") per-GPU share at 8 GPUs: 12.5M of 100M vectors, 1000 queries, top-1000
     "c4": (12_500_000, 768, 1000, 1000, "cosine"),
+    # the reference's production call (scripts/done/sim.sh: -mp False): 64 patch tokens per item, one weighted
+    # query, combine = min; 1M bank rows = 15625 items
+    "l64": (1_000_000, 768, 1, 100, "cosine"),
 }
+TOKENS = {"l64": 64}
 
 
 def read_peaks():
@@ -58,13 +62,12 @@ def read_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def read_traffic(path):
+def read_traffic(key):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the scoring kernel, from the committed
-    ncu --set full capture (profiles/traffic.json), or None."""
+    ncu --set full capture of the SAME workload (profiles/traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        d = json.load(open(p))
-        return d.get("simt" if path == "simt" else "tensor")
+        return json.load(open(p)).get(key)
     except Exception:
         return None
 
@@ -208,18 +211,19 @@ def run_reference(args, wl):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def build_bank(n_rows, D, dev, row0_chunk=0, dtype="bf16"):
+def build_bank(n_rows, D, dev, row0_chunk=0, dtype="bf16", L=1):
     """Device-generated synthetic shard: chunks [row0_chunk, ...) of the global synthetic bank,
-    normalised with the statistics of the first 512 rows of global chunk 0 on every rank."""
+    normalised with the statistics of the first 512 rows of global chunk 0 on every rank.
+    L > 1: every L consecutive rows form one item of L patch tokens (n_rows counts rows)."""
     from sky_embeddings_b200 import Bank, synth
-    bank = Bank(n_rows, 1, D, dtype, dev)
+    bank = Bank(n_rows // L, L, D, dtype, dev)
     first = synth.device_bank_chunk(0, 512, D, dev)
-    bank.fit_norm(first)
+    bank.fit_norm(first.reshape(512 // L, L, D))
     done = 0
     c = row0_chunk
     while done < n_rows:
         rows = min(synth.CHUNK_ROWS, n_rows - done)
-        bank.upload(synth.device_bank_chunk(c, rows, D, dev), done)
+        bank.upload(synth.device_bank_chunk(c, rows, D, dev).reshape(rows // L, L, D), done // L)
         done += rows
         c += 1
     return bank.finalize()
@@ -241,9 +245,10 @@ def run_gpu(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_bank, D, Q, k, metric = wl
+    L = TOKENS.get(args.workload, 1)
     chunks_per_rank = (n_bank + synth.CHUNK_ROWS - 1) // synth.CHUNK_ROWS
     row_lo = rank * n_bank
-    bank = build_bank(n_bank, D, dev, row0_chunk=rank * chunks_per_rank, dtype=args.bank_dtype)
+    bank = build_bank(n_bank, D, dev, row0_chunk=rank * chunks_per_rank, dtype=args.bank_dtype, L=L)
     esz = 2 if args.bank_dtype == "bf16" else 4
 
     # queries: planted neighbours of rows of THIS process's rank-0 shard layout (same on every rank:
@@ -298,7 +303,7 @@ def run_gpu(args, wl):
     # correctness gate before timing: the planted rows must come back first on rank 0's shard
     s, i = step_device()
     torch.cuda.synchronize()
-    if not int(os.environ.get("SKY_TC_DEBUG", "0")):      # profiling experiments disable parts of the kernel
+    if L == 1 and not int(os.environ.get("SKY_TC_DEBUG", "0")):      # profiling experiments disable parts of the kernel
         assert i[:, 0].cpu().tolist() == planted, "planted nearest neighbours not returned: refusing to time a wrong kernel"
 
     for _ in range(max(args.warmup, 3)):
@@ -377,7 +382,8 @@ def run_gpu(args, wl):
                            "pinned H2D + sky_search + NCCL all-gather + sky_merge_candidates + D2H"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": read_traffic("tensor" if use_tc else "simt"),
+                         "frac": achieved / peak if peak else None, "traffic": read_traffic("tensor" if (use_tc and args.workload == "c2") else
+                                                 ("stream_fp32_q1" if (args.workload == "q1" and args.bank_dtype == "fp32") else "none")),
                          "kernel": "tc_search_kernel<64>" if use_tc else "stream_search_kernel",
                          "kernel_ms": kern_avg_ms, "kernel_launches": n_kern, "algorithmic_bytes": algo_bytes,
                          "peak_source": peak_src, "kernel_share_of_step": kern_avg_ms * (n_kern / args.steps) / ms_step},

@@ -3,7 +3,7 @@ set -u
 mkdir -p gpurun_out
 run() { # label, env...
   label=$1; shift
-  for wl in ${WLS:-q1}; do for dt in ${DTS:-bf16 fp32}; do
+  for wl in ${WLS:-q1 q4}; do for dt in ${DTS:-bf16 fp32}; do
     env "$@" timeout 200 python bench.py --workload $wl --bank-dtype $dt --path simt --steps 30 --warmup 5 --no-cpu ${EXTRA:-} > gpurun_out/sw.json 2> gpurun_out/sw.err
     python - <<PY
 import json
@@ -14,5 +14,5 @@ except Exception as e: print("$label $wl $dt ERR", e, open("gpurun_out/sw.err").
 PY
   done; done
 }
-run base X=1
-EXTRA=--weighted run weighted X=1
+run ${LABEL:-base} X=1
+EXTRA=--weighted run ${LABEL:-base}_weighted X=1

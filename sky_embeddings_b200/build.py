@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [cc, *ARCH, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [cc, *ARCH, *FLAGS, *os.environ.get("SKY_NVCC_DEFS", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

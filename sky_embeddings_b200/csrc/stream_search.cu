@@ -61,6 +61,13 @@ __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
 }
 __device__ __forceinline__ float f2_lo(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
 __device__ __forceinline__ float f2_hi(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+#ifdef SKY_SCALAR_F2      // experiment: scalar FFMA / FMUL / FADD instead of the packed forms
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    return f2_pack(fmaf(f2_lo(a), f2_lo(b), f2_lo(c)), fmaf(f2_hi(a), f2_hi(b), f2_hi(c)));
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { return f2_pack(f2_lo(a) * f2_lo(b), f2_hi(a) * f2_hi(b)); }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { return f2_pack(f2_lo(a) - f2_lo(b), f2_hi(a) - f2_hi(b)); }
+#else
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
     uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
 }
@@ -70,6 +77,7 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
     uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
 }
+#endif
 
 __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile(
