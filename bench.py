@@ -44,6 +44,8 @@ WORKLOADS = {
     "c3s": (1_000_000, 768, 4096, 100, "MSE"),
     # BASELINE configs[3] ("C4") per-GPU share at 8 GPUs: 12.5M of 100M vectors, 1000 queries, top-1000
     "c4": (12_500_000, 768, 1000, 1000, "cosine"),
+    # C3 on 8 GPUs: the 10M-vector bank row-sharded, 1.25M vectors per GPU
+    "c3g8": (1_250_000, 768, 4096, 100, "MSE"),
     # the reference's production call (scripts/done/sim.sh: -mp False): 64 patch tokens per item, one weighted
     # query, combine = min; 1M bank rows = 15625 items
     "l64": (1_000_000, 768, 1, 100, "cosine"),
