@@ -247,33 +247,32 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
                 if (p.debug & 4) mbits = 0;
                 mbits = valid ? mbits : 0u;
-                // columns beyond the real queries carry a +inf bound and never pass
-                uint32_t cols = __reduce_or_sync(0xffffffffu, mbits);
+                // EXACT PATH (rare once bounds exist): every lane walks its own survivors -- the warp runs as many
+                // rounds as its busiest lane has bits; columns beyond the real queries carry a +inf bound and never pass
 #pragma unroll 1
-                while (cols) {
-                    const int j = __ffs(cols) - 1;
-                    cols &= cols - 1;
+                while (mbits) {
+                    const int j = __ffs(mbits) - 1;
+                    mbits &= mbits - 1;
+                    // vv[j] by a 5-level select tree (depth 5 instead of a 32-deep chain)
+                    uint32_t s16[16], s8[8], s4[4], s2[2];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s16[i] = (j & 1) ? vv[2 * i + 1] : vv[2 * i];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s8[i] = (j & 2) ? s16[2 * i + 1] : s16[2 * i];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s4[i] = (j & 4) ? s8[2 * i + 1] : s8[2 * i];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) s2[i] = (j & 8) ? s4[2 * i + 1] : s4[2 * i];
+                    const float dot = __uint_as_float((j & 16) ? s2[1] : s2[0]);
                     const int q = g * kTbBN + c * 32 + j;
                     const int qi = buf * kTbBN + c * 32 + j;
-                    bool pass = (mbits >> j) & 1u;
-                    uint64_t comp = 0;
-                    if (pass) {
-                        float dot = 0.f;
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) dot = (jj == j) ? __uint_as_float(vv[jj]) : dot;
-                        const float qcv = sQc[qi];
-                        const float sv = largest ? dot / fmaf(qcv, mx, 1e-6f) : (qcv - 2.0f * dot + rn) * p.inv_dd;
-                        comp = make_composite(score_to_key(sv, largest), static_cast<uint32_t>(row));
-                        pass = comp > sTau[qi];
-                    }
-                    const uint32_t pm = (p.debug & 16) ? 0u : __ballot_sync(0xffffffffu, pass);
-                    if (pm) {
-                        int basepos = 0;
-                        const int leader = __ffs(pm) - 1;
-                        if (lane == leader) basepos = static_cast<int>(atoms_add_u32(smem_addr(&sCnt[qi]), static_cast<uint32_t>(__popc(pm))));
-                        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+                    const float qcv = sQc[qi];
+                    const float sv = largest ? dot / fmaf(qcv, mx, 1e-6f) : (qcv - 2.0f * dot + rn) * p.inv_dd;
+                    const uint64_t comp = make_composite(score_to_key(sv, largest), static_cast<uint32_t>(row));
+                    if (comp > sTau[qi] && !(p.debug & 16)) {
                         // cap >= k + 256 and at most 128 rows per visit: the list cannot overflow before the check below
-                        if (pass) st_cg_u64(my_lists + static_cast<size_t>(q) * p.cap + basepos + __popc(pm & ((1u << lane) - 1u)), comp);
+                        const uint32_t pos = atoms_add_u32(smem_addr(&sCnt[qi]), 1u);
+                        st_cg_u64(my_lists + static_cast<size_t>(q) * p.cap + pos, comp);
                         inserted = true;
                     }
                 }

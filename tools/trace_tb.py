@@ -26,5 +26,5 @@ for e in range(4):
         e, np.median(per), np.median(b[:, 1] - b[:, 0]), (b[:, 1] - b[:, 0]).mean(), np.median(b[:, 2] - b[:, 1]), (b[:, 2] - b[:, 1]).mean(),
         np.median(b[:, 3] - b[:, 2]), (b[:, 3] - b[:, 2]).mean(), b[:, 4].mean()))
 t0 = a[:, :, 0].min()
-for v in range(100, 106):
+for v in range(min(100, len(a) - 6), min(106, len(a))):
     print("visit", v, " ".join("[e%d s=%d r=%d c=%d t=%d]" % (e, a[v, e, 0] - t0, a[v, e, 1] - a[v, e, 0], a[v, e, 2] - a[v, e, 1], a[v, e, 3] - a[v, e, 2]) for e in range(4)))
