@@ -43,6 +43,7 @@ struct TbParams {
     int Qp, nq, cap, k, groups, metric, kblocks;
     int64_t rows;              // valid bank rows
     int tile0, tile1;          // tiles [tile0, tile1) of this phase
+    int dense;                 // first phase: no bound exists, every row is a candidate -> lists are written densely
     int debug;                 // experiments: bit0 epilogue only drains TMEM, bit1 no MMA issue
     float inv_dd;
 };
@@ -228,6 +229,27 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             // one 32-column chunk: conservative pre-filter in the space of the accumulator (one FMA / ADD and one
             // compare per score, coefficients read with 128-bit shared loads issued up front), then the rare exact path
             auto process = [&](const uint32_t (&vv)[32], int c) {
+                if (p.dense) {
+                    // FIRST PHASE: everything is a candidate.  No filter, no atomics: row r of the tile goes to slot r
+                    // of the (empty) list of every query, 32 lanes = 256 contiguous bytes per store.
+                    const float4* pqc = reinterpret_cast<const float4*>(sQc + buf * kTbBN + c * 32);
+                    float4 qv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) qv[i] = pqc[i];
+                    uint64_t* dst = my_lists + static_cast<size_t>(g * kTbBN + c * 32) * p.cap + quarter * 32 + lane;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float qc4[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float dot = __uint_as_float(vv[i * 4 + u]);
+                            const float sv = largest ? dot / fmaf(qc4[u], mx, 1e-6f) : (qc4[u] - 2.0f * dot + rn) * p.inv_dd;
+                            const uint64_t comp = valid ? make_composite(score_to_key(sv, largest), static_cast<uint32_t>(row)) : 0ull;
+                            st_cg_u64(dst + static_cast<size_t>(i * 4 + u) * p.cap, comp);
+                        }
+                    }
+                    return;
+                }
                 const float4* pb1 = reinterpret_cast<const float4*>(sB1 + buf * kTbBN + c * 32);
                 const float4* pb2 = reinterpret_cast<const float4*>(sB2 + buf * kTbBN + c * 32);
                 float4 c1[8], c2[8];
@@ -299,7 +321,10 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             TB_TRACE(4, inserted ? 1 : 0);
             // write the fills back; lists of this group that could not take another 128 rows are pruned in place
             // to their k best (rare once bounds exist), which also yields a CTA-local bound
-            if (!(p.debug & 8) && named_bar_or(3, kTbEpiThreads, inserted)) {
+            if (p.dense) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) st_cg_i32(my_counts + g * kTbBN + et + j * 128, kTileRows);
+            } else if (!(p.debug & 8) && named_bar_or(3, kTbEpiThreads, inserted)) {
                 // warp e owns queries [64 e, 64 e + 64) of the group; lane handles two of them
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -378,7 +403,7 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
     uint64_t* pool = sel + kpad;                              // [kMpPool]
-    uint64_t* extra = (kMpPool > 2 * kMpSample) ? pool + kMpPool : nullptr;   // [kMpSample] survivors of the sampled pre-select
+    uint64_t* extra = pool + kMpPool;                         // [kMpSample] survivors of the sampled pre-select
     __shared__ uint32_t hist[256];
     __shared__ uint32_t scratch[4];
     __shared__ uint32_t npool;
@@ -412,38 +437,49 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
         if (lane == 0) npool = static_cast<uint32_t>(run);
     }
     __syncthreads();
+    const int np = static_cast<int>(npool);          // all candidates: carry + every list
+    // gather: everything if it fits the pool, else the first kMpPool candidates (a sample)
     for (int p = warp; p < P; p += nwarps) {
         const int n = s_n[p], o = s_off[p];
         const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
-        for (int i = lane; i < n; i += 32)
-            if (o + i < kMpPool) pool[o + i] = e[i];
+        for (int i = lane; i < n && o + i < kMpPool; i += 32) pool[o + i] = e[i];
     }
     __syncthreads();
-    const int np = static_cast<int>(npool);
+    bool done = false;
     if (np <= kMpPool) {
-        bool done = false;
-        if (np > 2 * kMpSample && extra != nullptr) {
-            // big pool (first phase: every row of every CTA): select on a sample first -- its k-th best is a lower
-            // bound of the real one -- then keep only what beats it and finish on the few survivors
-            block_select_sort([&](int j) { return pool[j]; }, kMpSample, k, kpad, sel, hist, scratch);
-            __syncthreads();
-            const uint64_t tau0 = sel[k - 1];
-            __shared__ uint32_t nkeep;
-            if (tid == 0) nkeep = 0;
-            __syncthreads();
-            for (int j = tid; j < np; j += kMpThreads) {
-                const uint64_t v = pool[j];
-                if (v >= tau0 && v != 0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < kMpSample) extra[pos] = v; }
+        block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch);
+        done = true;
+    } else {
+        // big candidate set (first phase: every row of every CTA): the k-th best of the sample is a lower bound of
+        // the real one -- stream all candidates once more, keep what beats it, finish on the few survivors
+        block_select_sort([&](int j) { return pool[j]; }, kMpPool, k, kpad, sel, hist, scratch);
+        __syncthreads();
+        const uint64_t tau0 = sel[k - 1];
+        __shared__ uint32_t nkeep;
+        if (tid == 0) nkeep = 0;
+        __syncthreads();
+        if (tau0 != 0) {
+            for (int j = tid; j < k; j += kMpThreads) {
+                const uint64_t v = cq[j];
+                if (v >= tau0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < kMpSample) extra[pos] = v; }
+            }
+            for (int p = warp; p < P; p += nwarps) {
+                const int n = s_n[p];
+                const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
+                for (int i = lane; i < n; i += 32) {
+                    const uint64_t v = e[i];
+                    if (v >= tau0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < kMpSample) extra[pos] = v; }
+                }
             }
             __syncthreads();
-            if (tau0 != 0 && nkeep <= kMpSample) {
+            if (nkeep <= kMpSample) {
                 block_select_sort([&](int j) { return extra[j]; }, static_cast<int>(nkeep), k, kpad, sel, hist, scratch);
                 done = true;
             }
-            __syncthreads();
         }
-        if (!done) block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch);
-    } else {
+        __syncthreads();
+    }
+    if (!done) {
         // adversarial order / huge k: more candidates than the pool holds -> select straight from L2
         auto fetch = [&](int j) -> uint64_t {
             if (j < k) return cq[j];
@@ -560,13 +596,17 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     int t0 = 0;
     int per_cta = 1;
     bool first = true;
+    int growth = 4;       // phase sizes 1, 1, 4, 16, ... tiles per CTA: fewer merges, a few more survivors per phase
     { static const char* e = getenv("SKY_TB_PHASE0"); if (e && atoi(e) >= 1) per_cta = atoi(e); }
+    { static const char* e = getenv("SKY_TB_GROWTH"); if (e && atoi(e) >= 2) growth = atoi(e); }
     while (t0 < num_tiles) {
         int t1 = t0 + per_cta * P;
         if (t1 > num_tiles || num_tiles - t1 < P) t1 = num_tiles;      // fold a short tail into this phase
         batch_bounds_kernel<<<(Qp + 255) / 256, 256, 0, st>>>(tauc, qconst, Q, Qp, metric, dd, b1, b2);
         SKY_LAUNCH_CHECK("batch_bounds_kernel");
         p.tile0 = t0; p.tile1 = t1;
+        // dense first phase: one tile per CTA into empty lists (a longer first phase keeps the filtered path)
+        p.dense = (first && per_cta == 1 && t1 - t0 <= P) ? 1 : 0;
         const int grid = (t1 - t0) < P ? (t1 - t0) : P;
         prof_mark(b, st);
         if (metric == SKY_COSINE) tc_batch_kernel<true><<<grid, kTbThreads, smem, st>>>(b->tmap_bank, tmq, p);
@@ -574,16 +614,20 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
         prof_mark(b, st);
         SKY_LAUNCH_CHECK("tc_batch_kernel");
         const int last = t1 == num_tiles ? 1 : 0;
-        // candidate pool in shared memory: the first phase admits every row (128 per CTA per query), later ones few
-        int pool = first ? (grid * kTileRows + k) : 4096;
-        const int extra = pool > 2 * kMpSample ? kMpSample : 0;
-        if (static_cast<size_t>(kpad + pool + extra) * 8 > 196 * 1024) pool = (196 * 1024) / 8 - kpad - extra;
-        const size_t msmem = static_cast<size_t>(kpad + pool + extra) * 8;
+        // sample pool of the merge: large enough that the k-th best of the sample keeps fewer than kMpSample of
+        // all candidates (first phase: every row of the phase's tiles is one)
+        int pool = 4096;
+        if (first) {
+            const int64_t np_max = static_cast<int64_t>(grid) * kTileRows + k;
+            const int64_t want = round_up(2 * np_max * k / kMpSample, 1024);
+            pool = static_cast<int>(want < 4096 ? 4096 : (want > 16384 ? 16384 : want));
+        }
+        const size_t msmem = static_cast<size_t>(kpad + pool + kMpSample) * 8;
         merge_phase_kernel<<<Qp, kMpThreads, msmem, st>>>(carry, tauc, lists, counts, lthr, P, Qp, cap, k, kpad, pool,
                                                          metric_largest(metric) ? 1 : 0, last, Q, idx_offset, out_scores, out_idx);
         SKY_LAUNCH_CHECK("merge_phase_kernel");
         t0 = t1;
-        if (!first) per_cta *= 2;
+        if (!first) per_cta *= growth;
         first = false;
     }
     return SKY_OK;
