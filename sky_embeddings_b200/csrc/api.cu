@@ -344,8 +344,23 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
     if (b->pixel) return set_error(SKY_ERR_STATE, "this is a pixel bank: use sky_search_pixels");
     if (!b->finalized) return set_error(SKY_ERR_STATE, "bank is not finalized");
     const bool tc_ok = tc_supported(b, metric, w != nullptr, n_top_sims);
-    if (path == SKY_PATH_TENSOR && !tc_ok)
-        return set_error(SKY_ERR_UNSUPPORTED, "tensor path needs a bf16 bank, L=1, cosine/MSE, no weights, no n_top_sims");
+    // queries with per-feature weights: second contraction against the squared tile, made on chip (K2w)
+    const bool tw_ok = tc_weighted_supported(b, metric, w != nullptr, n_top_sims);
+    if (path == SKY_PATH_TENSOR && !tc_ok && !tw_ok)
+        return set_error(SKY_ERR_UNSUPPORTED, "tensor path needs a bf16 bank, L=1, cosine/MSE, no n_top_sims");
+    if (tw_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q >= 2))) {
+        SearchState sw;
+        const int grid = tc_grid(b);
+        int rcw = plan_state(b, grid, Q, k, grid, &sw);
+        if (rcw) return rcw;
+        rcw = ensure_ws2(b, tc_weighted_scratch_bytes(b));
+        if (rcw) return rcw;
+        rcw = launch_init_state(sw, grid, st);
+        if (rcw) return rcw;
+        rcw = launch_tc_weighted(b, t, w, Q, metric, sw, st);
+        if (rcw) return rcw;
+        return launch_merge_lists(sw, metric, idx_offset, out_scores, out_idx, st);
+    }
     // small query batches stay on the streaming SIMT kernel (HBM bound there); larger ones need MMA
     const bool use_tc = tc_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q >= 2));
     // large query batches: the GEMM-shaped kernel (bank tile reused by all query groups through L2)
@@ -418,7 +433,9 @@ int sky_search_host(sky_bank_t* b, const float* h_t, const float* h_w, int Q, in
     const size_t sb = static_cast<size_t>(Q) * k * sizeof(float);
     const size_t ib = static_cast<size_t>(Q) * k * sizeof(int64_t);
     // staging lives behind the tensor-path scratch in ws2
-    const size_t off0 = static_cast<size_t>(round_up(static_cast<int64_t>(tc_scratch_bytes(b, Q)), 256));
+    size_t scratch = tc_scratch_bytes(b, Q);
+    if (tc_weighted_scratch_bytes(b) > scratch) scratch = tc_weighted_scratch_bytes(b);
+    const size_t off0 = static_cast<size_t>(round_up(static_cast<int64_t>(scratch), 256));
     int rc = ensure_ws2(b, off0 + 2 * round_up(qb, 256) + round_up(sb, 256) + round_up(ib, 256));
     if (rc) return rc;
     unsigned char* p = reinterpret_cast<unsigned char*>(b->ws2) + off0;

@@ -1,0 +1,414 @@
+// tc_weighted.cu -- K2w: tcgen05 scorer for queries WITH per-feature weights (the reference's default,
+// use_weights=True in both drivers: similarity_search.py:170, sky_sim_search.py:163).
+//
+// Contraction forms of the weighted metrics, a = w o t:
+//   cosine  utils/similarity.py:163-170   s = a.z / ( sqrt(sum w t^2) sqrt(w.(z o z)) + 1e-6 )
+//   MSE     utils/similarity.py:188-192   s = ( sum w t^2 - 2 a.z + w.(z o z) ) / (D sum w)
+// Two contractions per bank tile: D1 = Z A^T (A = [a_q]) and D2 = (Z o Z) W^T (W = [w_q]).  The bank holds
+// only Z; the squared tile is made ON CHIP: four "squarer" warps read every 16 KB stage the producers
+// land (thread = bank row), square it with packed bf16 multiplies and store it to TENSOR MEMORY with
+// tcgen05.st; the second MMA takes its A operand from there (no shared memory for Z o Z, so the ring stays
+// 6 stages deep).  HBM traffic is one pass over the bank for up to 64 weighted queries -- HBM bound like K2.  Candidate sink, grid-wide bound exchange and merge are shared with K1/K2.
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
+#include "bank.cuh"
+#include "ptx.cuh"
+#include "topk.cuh"
+
+namespace sky {
+
+constexpr int kTwBN = 64;                        // queries per launch
+constexpr int kTwProducerWarps = 4;              // warps 0-3: cp.async bank stream (+ TMA of the query k-blocks)
+constexpr int kTwSquareWarp0 = 4;                // warps 4-7: z -> z o z
+constexpr int kTwEpiWarp0 = 8;                   // warps 8-11: epilogue (warp & 3 = TMEM lane quarter)
+constexpr int kTwMmaWarp = 12;
+constexpr int kTwXchgWarp = 13;
+constexpr int kTwThreads = 14 * 32;
+constexpr int kTwProducers = kTwProducerWarps * 32;
+constexpr int kTwStageA = kTileRows * 128;       // 16 KB
+constexpr int kTwStageB = kTwBN * 128;           // 8 KB
+constexpr int kTwStage = kTwStageA + 2 * kTwStageB;       // A | Ba | Bw = 32 KB
+constexpr int kTwStages = 6;
+constexpr int kTwSqCols = 32;                    // TMEM columns of one squared k-block: 64 bf16 per row, two per column
+constexpr int kTwSqBase = 4 * kTwBN;             // behind the 2 x (D1 | D2) accumulators
+
+struct TwParams {
+    const unsigned char* bank;
+    const float* qc1;          // [64] cosine: sqrt(sum w t^2); MSE: sum w t^2
+    const float* qc2;          // [64] MSE: 1 / (D sum w); cosine: unused
+    uint64_t* lists; int* counts; uint32_t* gtop; uint32_t* gtau;
+    int p_stride, Qtot, q0, nq, cap, k, use_gtau;
+    int64_t rows;
+    int num_tiles, kblocks;
+    unsigned long long bank_policy;
+    int debug;                 // experiments: bit0 squarers only signal, bit1 no second MMA, bit2 epilogue only drains TMEM
+};
+
+__device__ __forceinline__ void tw_cp_async_16(uint32_t smem_dst, const void* gsrc, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "l"(policy) : "memory");
+}
+
+template <bool COS>
+__global__ void __launch_bounds__(kTwThreads, 1)
+tc_weighted_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const TwParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sStage = base;                                                   // [stages][A | Ba | Bw]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + kTwStages * kTwStage);   // producers -> squarers / MMA
+    uint64_t* sq_bar = full_bar + kTwStages;                                        // squarers -> MMA
+    uint64_t* empty_bar = sq_bar + kTwStages;                                       // MMA -> producers
+    uint64_t* tmem_full = empty_bar + kTwStages;                                    // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                                           // [2]
+    unsigned long long* sThr = reinterpret_cast<unsigned long long*>(tmem_empty + 2);   // [64]
+    float* sQ1 = reinterpret_cast<float*>(sThr + kTwBN);
+    float* sQ2 = sQ1 + kTwBN;
+    float* sThrF = sQ2 + kTwBN;
+    int* sCnt = reinterpret_cast<int*>(sThrF + kTwBN);
+    uint32_t* sLmax = reinterpret_cast<uint32_t*>(sCnt + kTwBN);
+    uint32_t* sHist = sLmax + kTwBN;                                                // [4][256]
+    uint32_t* sTmemBase = sHist + 4 * 256;
+    volatile int* sTilesDone = reinterpret_cast<volatile int*>(sTmemBase + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool largest = COS;
+    const int KB = p.kblocks;
+    const int my_tiles = (p.num_tiles > static_cast<int>(blockIdx.x))
+                             ? (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+    auto tile_of = [&](int it) -> int { return static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x); };
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_w);
+        for (int s = 0; s < kTwStages; ++s) {
+            ptx::mbar_init(&full_bar[s], kTwProducers + 1);      // 128 cp.async arrivals + the TMA issuer's expect_tx
+            ptx::mbar_init(&sq_bar[s], 128);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
+        ptx::fence_barrier_init();
+        *sTilesDone = 0;
+    }
+    if (warp == kTwMmaWarp) {
+        ptx::tmem_alloc(sTmemBase, 512);                         // 2 x (D1 | D2) accumulators + 6 squared k-blocks
+        ptx::tmem_relinquish();
+    }
+    for (int q = tid; q < kTwBN; q += kTwThreads) {
+        sThr[q] = (q < p.nq) ? 0ull : ~0ull;
+        sThrF[q] = (q < p.nq) ? __uint_as_float(0x7FC00000u) : (largest ? INFINITY : -INFINITY);
+        sQ1[q] = p.qc1[q];
+        sQ2[q] = p.qc2[q];
+        sCnt[q] = 0;
+        sLmax[q] = 0;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *sTmemBase;
+
+    Sink sink;
+    sink.lists = p.lists + (static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0) * p.cap;
+    sink.thr = smem_addr(sThr); sink.thr_f = smem_addr(sThrF); sink.cnt = smem_addr(sCnt); sink.lmax = smem_addr(sLmax);
+    sink.cap = p.cap; sink.k = p.k; sink.largest = largest;
+
+    if (warp < kTwProducerWarps) {
+        // ===================== producers: bank stage by cp.async, query k-blocks by TMA =====================
+        uint32_t dst_off[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = j * kTwProducers + tid;                // 16-byte chunk of the [128][64] block
+            const int row = g >> 3, c = g & 7;
+            dst_off[j] = static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4));   // 128-byte swizzle
+        }
+        const uint32_t s0 = ptx::smem_u32(sStage);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const unsigned char* src = p.bank + (static_cast<size_t>(tile_of(it)) * KB) * kTwStageA + static_cast<size_t>(tid) * 16;
+            for (int kb = 0; kb < KB; ++kb) {
+                if (lane == 0) ptx::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+                __syncwarp();
+                const uint32_t dst = s0 + static_cast<uint32_t>(stage) * kTwStage;
+                if (tid == 0) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kTwStageB);
+                    unsigned char* sb = sStage + static_cast<size_t>(stage) * kTwStage + kTwStageA;
+                    ptx::tma_load_2d(&tmap_a, sb, &full_bar[stage], kb * kKBlock, 0, ptx::kEvictLast);
+                    ptx::tma_load_2d(&tmap_w, sb + kTwStageB, &full_bar[stage], kb * kKBlock, 0, ptx::kEvictLast);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    tw_cp_async_16(dst + dst_off[j], src + static_cast<size_t>(j) * kTwProducers * 16, p.bank_policy);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&full_bar[stage])) : "memory");
+                src += kTwStageA;
+                if (++stage == kTwStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp < kTwEpiWarp0) {
+        // ===================== squarers: (Z o Z) k-block -> tensor memory =====================
+        // thread = bank row of the tile (TMEM lane); its 64 bf16 sit in 8 swizzled 16-byte chunks of the stage
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t s0 = ptx::smem_u32(sStage) + row * 128;
+        const uint32_t sw = static_cast<uint32_t>(row & 7);
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kTwSqBase;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int total = my_tiles * KB;
+        for (int i = 0; i < total; ++i) {
+            ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);
+            // the previous MMAs that read this TMEM buffer retired before the producers refilled the stage (empty_bar)
+            if (p.debug & 1) { ptx::mbar_arrive(&sq_bar[stage]); if (++stage == kTwStages) { stage = 0; phase ^= 1; } continue; }
+            const uint32_t a = s0 + static_cast<uint32_t>(stage) * kTwStage;
+            uint32_t v[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3]) : "r"(a + ((c ^ sw) << 4)));
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+                __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&v[u]);
+                x = __hmul2(x, x);
+                v[u] = *reinterpret_cast<uint32_t*>(&x);
+            }
+            ptx::tmem_st_32x32b_x32(t0 + stage * kTwSqCols, v);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&sq_bar[stage]);
+            if (++stage == kTwStages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == kTwMmaWarp) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileRows, kTwBN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                ptx::mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1, 32);
+                ptx::tc_fence_after();
+                const uint32_t d1 = tmem_base + static_cast<uint32_t>(acc * 2 * kTwBN);
+                const uint32_t d2 = d1 + kTwBN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);    // bank stage + query k-blocks have landed
+                    ptx::mbar_wait_relaxed(&sq_bar[stage], phase, 20);      // and the squared copy is written
+                    ptx::fence_proxy_async();                               // cp.async (generic proxy) writes of A
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(sStage + static_cast<size_t>(stage) * kTwStage);
+                    const uint32_t ba_addr = a_addr + kTwStageA;
+                    const uint32_t bw_addr = ba_addr + kTwStageB;
+                    const uint32_t a2_tmem = tmem_base + kTwSqBase + stage * kTwSqCols;
+#pragma unroll
+                    for (int k = 0; k < kKBlock / 16; ++k) {
+                        ptx::umma_bf16(d1, ptx::make_sw128_kmajor_desc(a_addr + k * 32), ptx::make_sw128_kmajor_desc(ba_addr + k * 32),
+                                       idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(p.debug & 2)) ptx::umma_bf16_ts(d2, a2_tmem + k * 8, ptx::make_sw128_kmajor_desc(bw_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == kTwStages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else if (warp >= kTwEpiWarp0 && warp < kTwEpiWarp0 + 4) {
+        // ===================== epilogue =====================
+        const int e = warp - kTwEpiWarp0;
+        const int quarter = warp & 3;
+        const uint32_t hist = smem_addr(sHist + e * 256);
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = tile_of(it);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int64_t row = static_cast<int64_t>(tile) * kTileRows + quarter * 32 + lane;
+            const bool valid = row < p.rows;
+            if (lane == 0) ptx::mbar_wait_relaxed(&tmem_full[acc], acc_phase, 128);
+            __syncwarp();
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 2 * kTwBN);
+#pragma unroll 1
+            for (int c = 0; c < kTwBN / 32; ++c) {
+                uint32_t v1[32], v2[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c * 32, v1);
+                ptx::tmem_ld_32x32b_x32(taddr + kTwBN + c * 32, v2);
+                ptx::tmem_ld_wait();
+                if (c == kTwBN / 32 - 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+                }
+                if (p.debug & 4) continue;
+                auto score = [&](float d1, float d2, float q1, float q2) -> float {
+                    // cosine: the accumulated w.(z o z) can round slightly below zero for a near-null row
+                    return COS ? __fdividef(d1, fmaf(q1, sqrtf(fmaxf(d2, 0.f)), 1e-6f)) : (q1 - 2.0f * d1 + d2) * q2;
+                };
+                // FAST PATH: conservative pre-filter without square root or division.  Thresholds are read with vector
+                // loads and may be stale (they only tighten); NaN goes on to the exact test; padding queries never pass.
+                //   cosine: s >= th  <=>  d1 >= th (q1 sqrt(d2) + 1e-6); with f(x) = x |x| (monotone) this is implied by
+                //           f(d1 + 1e-6) >= f(th q1) d2, lowered by a few 1e-6 relative
+                //   MSE:    s <= th  <=>  (q1 - 2 d1 + d2) q2 <= th
+                uint32_t mbits = 0;
+                const uint32_t thf_addr = sink.thr_f + c * 32 * 4;
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    float th[4];
+                    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(th[0]), "=f"(th[1]), "=f"(th[2]), "=f"(th[3]) : "r"(thf_addr + g4 * 16) : "memory");
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = g4 * 4 + u, q = c * 32 + j;
+                        const float d1 = __uint_as_float(v1[j]), d2 = __uint_as_float(v2[j]);
+                        bool pass;
+                        if (COS) {
+                            const float x = d1 + 1e-6f, t2 = th[u] * sQ1[q];
+                            float rhs = t2 * fabsf(t2) * fmaxf(d2, 0.f);
+                            rhs = fmaf(-fabsf(rhs), 8e-6f, rhs);
+                            pass = !(x * fabsf(x) < rhs);
+                        } else {
+                            pass = !((sQ1[q] - 2.0f * d1 + d2) * sQ2[q] > th[u]);
+                        }
+                        mbits |= (pass ? 1u : 0u) << j;
+                    }
+                }
+                mbits = valid ? mbits : 0u;
+#pragma unroll 1
+                while (mbits) {
+                    const int j = __ffs(mbits) - 1;
+                    mbits &= mbits - 1;
+                    const int q = c * 32 + j;
+                    if (q >= p.nq) continue;
+                    uint32_t a16[16], a8[8], a4[4], a2[2], b16[16], b8[8], b4[4], b2[2];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { a16[i] = (j & 1) ? v1[2 * i + 1] : v1[2 * i]; b16[i] = (j & 1) ? v2[2 * i + 1] : v2[2 * i]; }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { a8[i] = (j & 2) ? a16[2 * i + 1] : a16[2 * i]; b8[i] = (j & 2) ? b16[2 * i + 1] : b16[2 * i]; }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { a4[i] = (j & 4) ? a8[2 * i + 1] : a8[2 * i]; b4[i] = (j & 4) ? b8[2 * i + 1] : b8[2 * i]; }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) { a2[i] = (j & 8) ? a4[2 * i + 1] : a4[2 * i]; b2[i] = (j & 8) ? b4[2 * i + 1] : b4[2 * i]; }
+                    const float d1 = __uint_as_float((j & 16) ? a2[1] : a2[0]);
+                    const float d2 = __uint_as_float((j & 16) ? b2[1] : b2[0]);
+                    const float sv = score(d1, d2, sQ1[q], sQ2[q]);
+                    sink_insert_one(sink, q, make_composite(score_to_key(sv, largest), static_cast<uint32_t>(row)));
+                }
+            }
+            ptx::named_bar_sync(1, 128);
+            sink_prune_if_full(sink, p.nq, e, 4, hist);
+            ptx::named_bar_sync(1, 128);
+            if (e == 0 && lane == 0) *sTilesDone = it + 1;
+        }
+        ptx::named_bar_sync(1, 128);
+        for (int q = e * 32 + lane; q < p.nq; q += 128) {
+            p.counts[static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q] = static_cast<int>(lds_u32(sink.cnt + q * 4));
+            const uint32_t mine = lds_u32(sink.lmax + q * 4);
+            if (p.use_gtau && mine) st_cg_u32(p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q, mine);
+        }
+    } else if (warp == kTwXchgWarp) {
+        // ===================== grid-wide bound exchange (as K2) =====================
+        if (p.use_gtau && my_tiles > 0) {
+            uint32_t* my_row = p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0;
+            const int rq = static_cast<int>(blockIdx.x) % p.nq;
+            int round = 0;
+            uint32_t last_pub[kTwBN / 32] = {};
+            uint32_t last_lo = 0;
+            while (*sTilesDone < my_tiles) {
+                exchange_publish_changed(sink, p.nq, my_row, last_pub);
+                const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot, p.k);
+                if (lane == 0 && lo > last_lo) atomicMax(p.gtau + p.q0 + rq, lo);
+                last_lo = lo > last_lo ? lo : last_lo;
+                for (int q = lane; q < p.nq; q += 32) exchange_apply(sink, q, ld_cg_u32(p.gtau + p.q0 + q));
+                ++round;
+                __nanosleep(round < 24 ? 200 : 3000);
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == kTwMmaWarp) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// a = w o t and w as bf16 operand matrices [64, Dp] (zero padded) + per-query constants
+__global__ void pack_weighted_kernel(const float* __restrict__ t, const float* __restrict__ w, int nq, int D, int Dp, int metric,
+                                     __nv_bfloat16* __restrict__ ba, __nv_bfloat16* __restrict__ bw,
+                                     float* __restrict__ qc1, float* __restrict__ qc2) {
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ double red[2][8];
+    double s_wtt = 0.0, s_w = 0.0;
+    for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
+        float tv = 0.f, wv = 0.f;
+        if (q < nq && d < D) { tv = t[static_cast<size_t>(q) * D + d]; wv = w[static_cast<size_t>(q) * D + d]; }
+        ba[static_cast<size_t>(q) * Dp + d] = __float2bfloat16_rn(wv * tv);
+        bw[static_cast<size_t>(q) * Dp + d] = __float2bfloat16_rn(wv);
+        s_wtt += static_cast<double>(wv * (tv * tv));
+        s_w += static_cast<double>(wv);
+    }
+    for (int off = 16; off > 0; off >>= 1) { s_wtt += __shfl_xor_sync(0xffffffffu, s_wtt, off); s_w += __shfl_xor_sync(0xffffffffu, s_w, off); }
+    if (lane == 0) { red[0][warp] = s_wtt; red[1][warp] = s_w; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < nw; ++i) { a += red[0][i]; b += red[1][i]; }
+        const float wtt = static_cast<float>(a), sw = static_cast<float>(b);
+        qc1[q] = (metric == SKY_COSINE) ? sqrtf(wtt) : wtt;
+        qc2[q] = (metric == SKY_COSINE) ? 0.f : 1.0f / (sw * static_cast<float>(D));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows);     // tc_search.cu
+
+bool tc_weighted_supported(const sky_bank* b, int metric, bool weighted, int n_top) {
+    return b->dtype == SKY_BF16 && b->L == 1 && weighted && n_top == 0 && (metric == SKY_COSINE || metric == SKY_MSE) && b->rows > 0;
+}
+
+size_t tc_weighted_scratch_bytes(const sky_bank* b) {
+    return 2 * static_cast<size_t>(kTwBN) * b->Dp * 2 + 2 * kTwBN * sizeof(float) + 512;
+}
+
+// scratch (bank->ws2): Ba [64, Dp] bf16 | Bw [64, Dp] bf16 | qc1 [64] | qc2 [64]; one launch per 64 queries
+int launch_tc_weighted(sky_bank* b, const float* t, const float* w, int Q, int metric, const SearchState& s, cudaStream_t st) {
+    unsigned char* ws = reinterpret_cast<unsigned char*>(b->ws2);
+    __nv_bfloat16* ba = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* bw = ba + static_cast<size_t>(kTwBN) * b->Dp;
+    float* qc1 = reinterpret_cast<float*>(ws + round_up(2 * static_cast<int64_t>(kTwBN) * b->Dp * 2, 256));
+    float* qc2 = qc1 + kTwBN;
+    const size_t smem = 1024 + static_cast<size_t>(kTwStages) * kTwStage + (3 * kTwStages + 4) * 8 + kTwBN * (8 + 5 * 4) + 4 * 256 * 4 + 64;
+    if (metric == SKY_COSINE) SKY_CUDA(cudaFuncSetAttribute(tc_weighted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    else SKY_CUDA(cudaFuncSetAttribute(tc_weighted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    for (int q0 = 0; q0 < Q; q0 += kTwBN) {
+        const int nq = (Q - q0 < kTwBN) ? (Q - q0) : kTwBN;
+        pack_weighted_kernel<<<kTwBN, 256, 0, st>>>(t + static_cast<size_t>(q0) * b->D, w + static_cast<size_t>(q0) * b->D, nq, b->D, b->Dp,
+                                                   metric, ba, bw, qc1, qc2);
+        SKY_LAUNCH_CHECK("pack_weighted_kernel");
+        CUtensorMap tma, tmw;
+        int rc = make_tmap_2d(&tma, ba, kTwBN, b->Dp, kTwBN);
+        if (rc) return rc;
+        rc = make_tmap_2d(&tmw, bw, kTwBN, b->Dp, kTwBN);
+        if (rc) return rc;
+        TwParams p;
+        p.bank = reinterpret_cast<const unsigned char*>(b->data);
+        p.qc1 = qc1; p.qc2 = qc2;
+        p.lists = s.lists; p.counts = s.counts; p.gtop = s.gtop; p.gtau = s.gtau;
+        p.p_stride = s.p_stride; p.Qtot = s.Qtot; p.q0 = q0; p.nq = nq; p.cap = s.cap; p.k = s.k; p.use_gtau = s.use_gtau;
+        p.rows = b->rows;
+        p.num_tiles = static_cast<int>((b->rows + kTileRows - 1) / kTileRows);
+        p.kblocks = b->Dp / kKBlock;
+        p.bank_policy = ptx::kEvictFirst;
+        { static const char* e = getenv("SKY_TW_DEBUG"); p.debug = e ? atoi(e) : 0; }
+        prof_mark(b, st);
+        if (metric == SKY_COSINE) tc_weighted_kernel<true><<<s.P, kTwThreads, smem, st>>>(tma, tmw, p);
+        else tc_weighted_kernel<false><<<s.P, kTwThreads, smem, st>>>(tma, tmw, p);
+        prof_mark(b, st);
+        SKY_LAUNCH_CHECK("tc_weighted_kernel");
+    }
+    return SKY_OK;
+}
+
+}  // namespace sky

@@ -275,7 +275,10 @@ def test_multi_query_weighted_patches(dev, dtype, rel, path, L):
     for metric in ("cosine", "MSE", "MAE"):
         for combine in ("mean", "min", "max"):
             for nts in ((None, 3) if L >= 3 else (None,)):
-                sc, ix = bank.search(t, w, k=k, metric=metric, combine=combine, n_top_sims=nts, path=path)
+                # L = 1 on a bf16 bank would go to the weighted tensor path under "auto" (bf16 operands): this test
+                # checks the fp32 arithmetic of the streaming scorer, the tensor path has its own test below
+                sc, ix = bank.search(t, w, k=k, metric=metric, combine=combine, n_top_sims=nts,
+                                     path=("simt" if (L == 1 and path == "auto") else path))
                 ref_s, ref_i = O.search(tn, wn, z, k, metric, combine, nts)
                 for q in range(Q):
                     ok, msg = O.check_topk_parity(sc[q].cpu().numpy(), ix[q].cpu().numpy(), ref_s[q], ref_i[q], rel)
@@ -583,4 +586,59 @@ def test_batch_path_adversarial_order_and_nan(dev):
             assert ok, f"{metric} q{q}: {msg}"
         if metric == "cosine":
             assert set(ix[0, :2].tolist()) == {11, 70000} and np.isnan(sc[0, :2]).all()
+    bank.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# weighted tensor path (K2w): per-query feature weights, second contraction against the on-chip squared tile
+# ------------------------------------------------------------------------------------------------
+def _weighted_model_scores(z_bf16, t, w, metric):
+    """What K2w computes, in float64: bf16(w t), bf16(w), bf16(z z) operands, fp32-free accumulation."""
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float64).numpy()
+    z = z_bf16.astype(np.float64)
+    a_b, w_b, z2_b = bf(w * t), bf(w), bf((z_bf16.astype(np.float32)) ** 2)
+    d1 = z @ a_b.T                                  # [N, Q]
+    d2 = z2_b @ w_b.T
+    wtt = (w.astype(np.float64) * t.astype(np.float64) ** 2).sum(1)[None, :]
+    if metric == "cosine":
+        return (d1 / (np.sqrt(wtt) * np.sqrt(np.maximum(d2, 0)) + 1e-6)).T
+    D = z.shape[1]
+    return ((wtt - 2 * d1 + d2) / (D * w.astype(np.float64).sum(1)[None, :])).T
+
+
+@pytest.mark.parametrize("metric", ["cosine", "MSE"])
+@pytest.mark.parametrize("n,Q,k,D", [(20000, 64, 100, 768), (777, 5, 10, 768), (130, 70, 100, 96), (33000, 130, 20, 256)])
+def test_weighted_tensor_path_vs_oracle(dev, metric, n, Q, k, D):
+    from sky_embeddings_b200 import Bank, synth
+    lat = synth.latents(n, 1, D, stream=301)
+    bank = Bank.from_latents(torch.from_numpy(lat).to(dev), norm_rows=64, dtype="bf16")
+    z = bank.download().cpu().numpy()[:, 0]
+    ts, ws = [], []
+    for q in range(Q):        # realistic queries: mean / inverse-variance weights of a noisy target group
+        grp = synth.target_group(z[:, None, :].astype(np.float32), [(37 * q + 3) % n, (91 * q + 5) % n], copies=6, noise=0.4, stream=310 + q)
+        tq, wq = O.target_features(grp)
+        ts.append(tq)
+        ws.append(wq)
+    t = np.stack(ts).astype(np.float32)
+    w = np.stack(ws).astype(np.float32)
+    sc, ix = bank.search(torch.from_numpy(t).to(dev), torch.from_numpy(w).to(dev), k=k, metric=metric, path="tensor")
+    sc, ix = sc.cpu().numpy(), ix.cpu().numpy()
+    model = _weighted_model_scores(z, t, w, metric)
+    ref_s, ref_i = O.search(t.astype(np.float64), w.astype(np.float64), z[:, None].astype(np.float64), k, metric, "min")
+    for q in range(Q):
+        ms, mi = O.topk(model[q], k, metric)
+        ok, msg = O.check_topk_parity(sc[q], ix[q], ms, mi, 5e-5, all_scores=model[q])
+        assert ok, f"weighted-tensor-vs-model n={n} q{q}: {msg}"
+        all_ref = O.item_scores(t[q].astype(np.float64), w[q].astype(np.float64), z[:, None].astype(np.float64), metric, "min")
+        # three bf16 operand roundings (w t, w, z z) average out over the features: 1e-3 at D >= 256, looser below
+        # the expanded MSE cancels (sum w t^2 - 2 a.z + w.(z z)): its bf16 operand error is relative to the size of the
+        # terms, i.e. to a typical score, not to the (small) score of a near neighbour -> scale-relative tolerance
+        # (sum w t^2 + w.(z z)) / (D sum w) is about twice a typical (median) score
+        scale = 2.0 * float(np.median(all_ref)) if metric == "MSE" else None
+        ok, msg = O.check_topk_parity(sc[q], ix[q], ref_s[q], ref_i[q], REL_BF16 if D >= 256 else 3e-3, all_scores=all_ref, scale=scale)
+        assert ok, f"weighted-tensor-vs-oracle n={n} q{q}: {msg}"
+    # "auto" takes the same path for Q >= 2 on a bf16 bank
+    sc2, ix2 = bank.search(torch.from_numpy(t).to(dev), torch.from_numpy(w).to(dev), k=k, metric=metric)
+    if Q >= 2:
+        assert np.array_equal(ix2.cpu().numpy(), ix)
     bank.close()
