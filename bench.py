@@ -235,8 +235,7 @@ def run_gpu(args, wl):
     import torch
     import torch.distributed as dist
     from sky_embeddings_b200 import _lib, synth
-    from sky_embeddings_b200.distributed import gather_candidates
-    from sky_embeddings_b200.engine import merge_candidates
+    from sky_embeddings_b200.distributed import CandidateExchange
 
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
@@ -272,12 +271,15 @@ def run_gpu(args, wl):
     out_s_host = torch.empty((Q, k), dtype=torch.float32).pin_memory()
     out_i_host = torch.empty((Q, k), dtype=torch.int64).pin_memory()
 
+    xchg = CandidateExchange(Q, k, dev) if world > 1 else None
+
     def step_device():
-        s, i = bank.search(t_dev, w_dev, k=k, metric=metric, path=args.path, idx_offset=row_lo)
-        if world > 1:
-            gs, gi = gather_candidates(s, i)
-            s, i = merge_candidates(gs, gi, k, metric)
-        return s, i
+        if world == 1:
+            return bank.search(t_dev, w_dev, k=k, metric=metric, path=args.path, idx_offset=row_lo)
+        # local top-k straight into the exchange buffer, ONE all-gather (scores + indices), in-place strided merge
+        bank.search(t_dev, w_dev, k=k, metric=metric, path=args.path, idx_offset=row_lo,
+                    out_scores=xchg.scores, out_idx=xchg.idx)
+        return xchg.merge(metric)
 
     def step_host():
         # public API with HOST buffers: H2D of the queries and D2H of the results inside the call
@@ -286,9 +288,8 @@ def run_gpu(args, wl):
                                     out_scores=out_s_host, out_idx=out_i_host)
         td = t_host.to(dev, non_blocking=True)
         wd = w_host.to(dev, non_blocking=True) if w_host is not None else None
-        s, i = bank.search(td, wd, k=k, metric=metric, path=args.path, idx_offset=row_lo)
-        gs, gi = gather_candidates(s, i)
-        s, i = merge_candidates(gs, gi, k, metric)
+        bank.search(td, wd, k=k, metric=metric, path=args.path, idx_offset=row_lo, out_scores=xchg.scores, out_idx=xchg.idx)
+        s, i = xchg.merge(metric)
         out_s_host.copy_(s, non_blocking=True)
         out_i_host.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -381,7 +382,7 @@ def run_gpu(args, wl):
             "e2e": {"value": world * Q / (e2e_step * 1e-3), "unit": "queries/s", "ms_per_step": e2e_step,
                     "h2d_bytes_per_step": t_host.numel() * 4 * (2 if args.weighted else 1), "d2h_bytes_per_step": Q * k * 12,
                     "api": "sky_search_host (C ABI, pinned host buffers)" if world == 1 else
-                           "pinned H2D + sky_search + NCCL all-gather + sky_merge_candidates + D2H"},
+                           "pinned H2D + sky_search + one NCCL all-gather + sky_merge_candidates_strided + D2H"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": read_traffic("tensor" if (use_tc and args.workload == "c2") else

@@ -152,6 +152,12 @@ SKY_API int sky_score_pixels(sky_bank_t* bank, const float* q, const unsigned ch
 SKY_API int sky_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int k_out,
                          int metric, float* out_scores, int64_t* out_idx, int device, void* stream);
 
+/* same, the R lists living in R per-rank blocks: list r starts stride_* ELEMENTS after list r-1 (the
+ * gathered buffer of ONE all-gather that carries a rank's scores and indices together). */
+SKY_API int sky_merge_candidates_strided(const float* scores, const int64_t* idx, int R, int Q, int k_in,
+                                 int64_t stride_scores, int64_t stride_idx, int k_out, int metric,
+                                 float* out_scores, int64_t* out_idx, int device, void* stream);
+
 /* Timing of the dominant (scoring) kernel of each search with CUDA events recorded on the launch
  * stream right around it: enable, run searches, then read (#launches, total ms); read synchronises. */
 SKY_API int sky_profile_enable(sky_bank_t* bank, int enable);

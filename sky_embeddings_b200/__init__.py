@@ -7,7 +7,7 @@ teaghan/sky_embeddings (utils/similarity.py as driven by similarity_search.py / 
 Everything numeric runs in libskysearch.so (hand-written sm_100a CUDA behind a C ABI,
 include/sky_search.h); importing the search API without the built library raises.
 """
-__all__ = ["Bank", "PixelBank", "merge_candidates", "ShardedBank", "sharded_search", "shard_range"]
+__all__ = ["Bank", "PixelBank", "bank_from_loader", "resident_simsearch", "merge_candidates", "ShardedBank", "sharded_search", "shard_range"]
 
 
 def __getattr__(name):
@@ -17,4 +17,7 @@ def __getattr__(name):
     if name in ("ShardedBank", "sharded_search", "shard_range"):
         from . import distributed
         return getattr(distributed, name)
+    if name in ("bank_from_loader", "resident_simsearch"):
+        from . import feeder
+        return getattr(feeder, name)
     raise AttributeError(name)

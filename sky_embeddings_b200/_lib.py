@@ -45,6 +45,7 @@ SIGNATURES = {
     "sky_search_pixels": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]),
     "sky_score_pixels": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _vp]),
     "sky_merge_candidates": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sky_merge_candidates_strided": (_i, [_vp, _vp, _i, _i, _i, _i64, _i64, _i, _i, _vp, _vp, _i, _vp]),
     "sky_profile_enable": (_i, [_vp, _i]),
     "sky_profile_read": (_i, [_vp, C.POINTER(_i64), C.POINTER(C.c_double), _i]),
     "sky_launch_count": (_i64, [_i]),

@@ -581,7 +581,21 @@ int sky_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, 
     if (R < 1 || Q < 0 || k_in < 1 || k_out < 1) return set_error(SKY_ERR_ARG, "bad merge shape");
     DeviceGuard g(device);
     if (!g.ok) return set_error(SKY_ERR_CUDA, "cudaSetDevice(%d) failed: no CUDA device, and there is no CPU fallback", device);
-    return launch_merge_candidates(scores, idx, R, Q, k_in, k_out, metric, out_scores, out_idx, static_cast<cudaStream_t>(stream));
+    return launch_merge_candidates(scores, idx, R, Q, k_in, 0, 0, k_out, metric, out_scores, out_idx, static_cast<cudaStream_t>(stream));
+}
+
+int sky_merge_candidates_strided(const float* scores, const int64_t* idx, int R, int Q, int k_in, int64_t stride_scores,
+                                 int64_t stride_idx, int k_out, int metric, float* out_scores, int64_t* out_idx, int device,
+                                 void* stream) {
+    if (!scores || !idx || !out_scores || !out_idx) return set_error(SKY_ERR_ARG, "NULL argument");
+    if (!valid_metric(metric)) return set_error(SKY_ERR_ARG, "unknown metric %d", metric);
+    if (R < 1 || Q < 0 || k_in < 1 || k_out < 1) return set_error(SKY_ERR_ARG, "bad merge shape");
+    if (stride_scores < static_cast<int64_t>(Q) * k_in || stride_idx < static_cast<int64_t>(Q) * k_in)
+        return set_error(SKY_ERR_ARG, "rank strides must cover Q * k_in elements");
+    DeviceGuard g(device);
+    if (!g.ok) return set_error(SKY_ERR_CUDA, "cudaSetDevice(%d) failed: no CUDA device, and there is no CPU fallback", device);
+    return launch_merge_candidates(scores, idx, R, Q, k_in, stride_scores, stride_idx, k_out, metric, out_scores, out_idx,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

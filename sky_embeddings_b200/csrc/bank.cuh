@@ -122,7 +122,7 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
 int launch_init_state(const SearchState& s, int p_active, cudaStream_t st);
 int launch_merge_lists(const SearchState& s, int metric, int64_t idx_offset, float* out_scores, int64_t* out_idx,
                        cudaStream_t st);
-int launch_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int k_out, int metric,
-                            float* out_scores, int64_t* out_idx, cudaStream_t st);
+int launch_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int64_t stride_s,
+                            int64_t stride_i, int k_out, int metric, float* out_scores, int64_t* out_idx, cudaStream_t st);
 
 }  // namespace sky

@@ -91,8 +91,8 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_candidates_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, int R, int Q, int k_in,
-                        int k_out, int kpad, int largest, float* __restrict__ out_scores,
-                        int64_t* __restrict__ out_idx) {
+                        int64_t stride_s, int64_t stride_i, int k_out, int kpad, int largest,
+                        float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
     __shared__ uint32_t hist[256];
@@ -101,14 +101,18 @@ merge_candidates_kernel(const float* __restrict__ scores, const int64_t* __restr
     const int n = R * k_in;
     // composite low word = position in the (rank-major) concatenation: lists are best-first with
     // ties by lower index and shards hold increasing row ranges, so position order == index order
-    auto src = [&](int j) -> size_t {
+    // list r of this query starts at r * stride (elements): dense [R, Q, k_in] or one gathered buffer per rank
+    auto src_s = [&](int j) -> size_t {
         const int r = j / k_in, i = j - r * k_in;
-        return (static_cast<size_t>(r) * Q + q) * k_in + i;
+        return static_cast<size_t>(r) * stride_s + static_cast<size_t>(q) * k_in + i;
+    };
+    auto src_i = [&](int j) -> size_t {
+        const int r = j / k_in, i = j - r * k_in;
+        return static_cast<size_t>(r) * stride_i + static_cast<size_t>(q) * k_in + i;
     };
     auto fetch = [&](int j) -> uint64_t {
-        const size_t s = src(j);
-        if (idx[s] < 0) return 0ull;
-        return make_composite(score_to_key(scores[s], largest != 0), static_cast<uint32_t>(j));
+        if (idx[src_i(j)] < 0) return 0ull;
+        return make_composite(score_to_key(scores[src_s(j)], largest != 0), static_cast<uint32_t>(j));
     };
     block_select_sort(fetch, n, k_out, kpad, sel, hist, scratch);
     __syncthreads();
@@ -120,9 +124,9 @@ merge_candidates_kernel(const float* __restrict__ scores, const int64_t* __restr
             *so = largest ? -INFINITY : INFINITY;
             *io = -1;
         } else {
-            const size_t s = src(static_cast<int>(composite_idx(c)));
-            *so = scores[s];
-            *io = idx[s];
+            const int j0 = static_cast<int>(composite_idx(c));
+            *so = scores[src_s(j0)];
+            *io = idx[src_i(j0)];
         }
     }
 }
@@ -153,14 +157,16 @@ int launch_merge_lists(const SearchState& s, int metric, int64_t idx_offset, flo
     return SKY_OK;
 }
 
-int launch_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int k_out, int metric,
-                            float* out_scores, int64_t* out_idx, cudaStream_t st) {
+int launch_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int64_t stride_s,
+                            int64_t stride_i, int k_out, int metric, float* out_scores, int64_t* out_idx, cudaStream_t st) {
     if (k_out > kMaxK) return set_error(SKY_ERR_UNSUPPORTED, "k=%d exceeds the merge limit %d", k_out, kMaxK);
     if (Q == 0) return SKY_OK;
     const int kpad = next_pow2(k_out);
     const size_t smem = static_cast<size_t>(kpad) * sizeof(uint64_t);
     SKY_CUDA(cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    merge_candidates_kernel<<<Q, kMergeThreads, smem, st>>>(scores, idx, R, Q, k_in, k_out, kpad,
+    if (stride_s <= 0) stride_s = static_cast<int64_t>(Q) * k_in;
+    if (stride_i <= 0) stride_i = static_cast<int64_t>(Q) * k_in;
+    merge_candidates_kernel<<<Q, kMergeThreads, smem, st>>>(scores, idx, R, Q, k_in, stride_s, stride_i, k_out, kpad,
                                                            metric_largest(metric) ? 1 : 0, out_scores, out_idx);
     SKY_LAUNCH_CHECK("merge_candidates_kernel");
     return SKY_OK;

@@ -47,6 +47,45 @@ def gather_candidates(scores, idx, group=None):
     return g_s, g_i
 
 
+class CandidateExchange:
+    """The exchange step of a sharded search with ONE collective: a rank's [Q, k] indices (i64) and scores (f32)
+    live in one preallocated device buffer, so a single NCCL all-gather moves both, and the merge kernel reads
+    the gathered per-rank blocks in place (sky_merge_candidates_strided) -- no packing or copy kernels."""
+
+    def __init__(self, Q, k, device, group=None, world=None):
+        self.Q, self.k, self.group = int(Q), int(k), group
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        n = self.Q * self.k
+        self.units = n + (n + 1) // 2                      # int64 units per rank: idx | scores (two f32 per unit)
+        self.local = torch.empty(self.units, dtype=torch.int64, device=device)
+        self.gathered = torch.empty(self.world * self.units, dtype=torch.int64, device=device)
+        self.idx = self.local[:n].view(self.Q, self.k)
+        self.scores = self.local[n:].view(torch.float32)[:n].view(self.Q, self.k)
+        self.out_scores = torch.empty((self.Q, self.k), dtype=torch.float32, device=device)
+        self.out_idx = torch.empty((self.Q, self.k), dtype=torch.int64, device=device)
+
+    def merge(self, metric):
+        """All-gather the local candidates (already written into .scores / .idx) and merge; returns the global
+        (scores, idx), identical on every rank."""
+        if self.world == 1:
+            return self.scores, self.idx
+        dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
+        return self.merge_gathered(metric)
+
+    def merge_gathered(self, metric):
+        """Merge the per-rank blocks already sitting in .gathered (rank r at [r * units, (r + 1) * units))."""
+        import ctypes as C
+        from . import _lib as L
+        from .engine import _stream
+        n = self.Q * self.k
+        base = self.gathered.data_ptr()
+        L.check(L.load().sky_merge_candidates_strided(
+            C.c_void_p(base + n * 8), C.c_void_p(base), self.world, self.Q, self.k, self.units * 2, self.units,
+            self.k, L.METRICS["cosine" if metric == "cosine" else "MSE"], C.c_void_p(self.out_scores.data_ptr()),
+            C.c_void_p(self.out_idx.data_ptr()), self.gathered.device.index, _stream(self.gathered.device)))
+        return self.out_scores, self.out_idx
+
+
 def sharded_search(local_search, k, metric, merge=None, group=None):
     """local_search() -> (scores [Q, k], idx [Q, k] with GLOBAL indices) on this rank's shard.
     Returns the global top-k on every rank.  `merge` defaults to the CUDA merge kernel."""
@@ -64,8 +103,18 @@ class ShardedBank:
 
     def __init__(self, bank, row_lo, n_total, group=None):
         self.bank, self.row_lo, self.n_total, self.group = bank, int(row_lo), int(n_total), group
+        self._xchg = None
 
     def search(self, t, w=None, k=100, metric="cosine", combine="min", n_top_sims=None, path="auto"):
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1 and t.is_cuda:
+            Q = 1 if t.dim() == 1 else t.shape[0]
+            if self._xchg is None or (self._xchg.Q, self._xchg.k) != (Q, k):
+                self._xchg = CandidateExchange(Q, k, self.bank.device, self.group)
+            x = self._xchg
+            self.bank.search(t, w, k, metric, combine, n_top_sims, path, idx_offset=self.row_lo,
+                             out_scores=x.scores, out_idx=x.idx)
+            s, i = x.merge(metric)
+            return s.clone(), i.clone()
         return sharded_search(
             lambda: self.bank.search(t, w, k, metric, combine, n_top_sims, path, idx_offset=self.row_lo),
             k, metric, group=self.group)

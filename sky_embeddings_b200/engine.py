@@ -186,8 +186,9 @@ class Bank:
         return t, w
 
     def search(self, t, w=None, k=100, metric="cosine", combine="min", n_top_sims=None, path="auto",
-               idx_offset=0):
-        """Exact top-k of every query over the bank.  Returns (scores [Q,k] f32, idx [Q,k] i64)."""
+               idx_offset=0, out_scores=None, out_idx=None):
+        """Exact top-k of every query over the bank.  Returns (scores [Q,k] f32, idx [Q,k] i64).
+        out_scores / out_idx: optional preallocated contiguous device outputs."""
         if metric not in L.METRICS:
             # the reference dies with UnboundLocalError here (utils/similarity.py:250-259)
             raise ValueError(f"unknown metric {metric!r}: expected 'cosine', 'MSE' or 'MAE'")
@@ -195,8 +196,10 @@ class Bank:
             raise ValueError(f"unknown combine {combine!r}: expected 'mean', 'min' or 'max'")
         t, w = self._qprep(t, w)
         Q = t.shape[0]
-        scores = torch.empty((Q, k), device=self.device, dtype=torch.float32)
-        idx = torch.empty((Q, k), device=self.device, dtype=torch.int64)
+        scores = torch.empty((Q, k), device=self.device, dtype=torch.float32) if out_scores is None else out_scores
+        idx = torch.empty((Q, k), device=self.device, dtype=torch.int64) if out_idx is None else out_idx
+        if scores.shape != (Q, k) or idx.shape != (Q, k) or not (scores.is_contiguous() and idx.is_contiguous()):
+            raise ValueError("out_scores / out_idx must be contiguous [Q, k] tensors")
         L.check(self.lib.sky_search(self._h, _ptr(t), _ptr(w) if w is not None else None, Q, L.METRICS[metric],
                                     L.COMBINES[combine], int(n_top_sims or 0), int(k), int(idx_offset),
                                     _ptr(scores), _ptr(idx), L.PATHS[path], _stream(self.device)))

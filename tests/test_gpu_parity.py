@@ -392,6 +392,15 @@ def test_sharded_equals_unsharded(dev):
         ms, mi = merge_candidates(torch.stack(parts_s), torch.stack(parts_i), k, metric)
         assert torch.equal(mi, i_full), metric
         assert torch.equal(ms, s_full), metric
+        # the one-collective exchange: each rank's (idx | scores) block as the all-gather would lay them out
+        from sky_embeddings_b200.distributed import CandidateExchange
+        x = CandidateExchange(Q, k, dev, world=world)
+        for r in range(world):
+            x.idx.copy_(parts_i[r])
+            x.scores.copy_(parts_s[r])
+            x.gathered[r * x.units:(r + 1) * x.units].copy_(x.local)
+        xs, xi = x.merge_gathered(metric)
+        assert torch.equal(xi, i_full) and torch.equal(xs, s_full), metric
     full.close()
 
 
@@ -642,3 +651,35 @@ def test_weighted_tensor_path_vs_oracle(dev, metric, n, Q, k, D):
     if Q >= 2:
         assert np.array_equal(ix2.cpu().numpy(), ix)
     bank.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# feeder: encoder output -> resident bank without the host round trip
+# ------------------------------------------------------------------------------------------------
+def test_feeder_resident_bank_matches_reference_goldens(dev):
+    """bank_from_loader + resident_simsearch reproduce the reference's mae_simsearch outputs (golden fixtures)
+    for every token mode x metric x combine, from ONE encoding pass per token mode."""
+    from sky_embeddings_b200 import bank_from_loader, resident_simsearch
+    g = G.load("simsearch_small")
+    bank_lat, tgt, bs, k = G.simsearch_inputs(g)
+    banks = {}
+    for name in g["names"]:
+        kw = G.parse_simsearch_name(str(name))
+        mode = (kw["max_pool"], kw["cls_token"])
+        if mode not in banks:
+            # capacity from the loader on the first mode, gathered-on-device path on the others
+            loader = _Loader(bank_lat, bs)
+            banks[mode] = bank_from_loader(_LatentStub(), loader, dev, max_pool=kw["max_pool"], cls_token=kw["cls_token"],
+                                           bank_dtype="fp32", n_items=(bank_lat.shape[0] if len(banks) == 0 else None),
+                                           keep_samples=True)
+        bank, ra, smp = banks[mode]
+        assert bank.n_items == bank_lat.shape[0] and ra.shape == (bank_lat.shape[0], 2)
+        bs_, idx, bra, sc = resident_simsearch(bank, torch.from_numpy(tgt), ra, smp, num_extra_tokens=1, n_save=k,
+                                               metric=kw["metric"], combine=kw["combine"], use_weights=kw["use_weights"],
+                                               max_pool=kw["max_pool"], cls_token=kw["cls_token"])
+        ok, msg = O.check_topk_parity(sc.cpu().numpy(), idx.cpu().numpy(), g[f"scores.{name}"], g[f"idx.{name}"], REL_F32)
+        assert ok, f"{name}: {msg}"
+        assert np.array_equal(bra[:, 0].cpu().numpy().astype(np.int64), idx.cpu().numpy())
+        assert np.array_equal(bs_.numpy(), bank_lat[idx.cpu().numpy()])
+    for bank, _, _ in banks.values():
+        bank.close()
