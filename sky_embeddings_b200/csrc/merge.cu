@@ -71,7 +71,9 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     }
     __syncthreads();
     const int np = static_cast<int>(npool);
-    if (np <= kPool) {
+    if (np <= kRankSortMax) {
+        block_rank_topk(pool, np, k, kpad, sel);
+    } else if (np <= kPool) {
         block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch);
     } else {
         // rare: too many survivors (adversarial order / massive ties) -> select straight from L2
@@ -114,7 +116,14 @@ merge_candidates_kernel(const float* __restrict__ scores, const int64_t* __restr
         if (idx[src_i(j)] < 0) return 0ull;
         return make_composite(score_to_key(scores[src_s(j)], largest != 0), static_cast<uint32_t>(j));
     };
-    block_select_sort(fetch, n, k_out, kpad, sel, hist, scratch);
+    if (n <= kRankSortMax) {
+        uint64_t* cand = sel + kpad;                          // [n] (dynamic smem sized by the launcher)
+        for (int j = tid; j < n; j += kMergeThreads) cand[j] = fetch(j);
+        __syncthreads();
+        block_rank_topk(cand, n, k_out, kpad, sel);
+    } else {
+        block_select_sort(fetch, n, k_out, kpad, sel, hist, scratch);
+    }
     __syncthreads();
     for (int j = tid; j < k_out; j += kMergeThreads) {
         const uint64_t c = sel[j];
@@ -162,7 +171,7 @@ int launch_merge_candidates(const float* scores, const int64_t* idx, int R, int 
     if (k_out > kMaxK) return set_error(SKY_ERR_UNSUPPORTED, "k=%d exceeds the merge limit %d", k_out, kMaxK);
     if (Q == 0) return SKY_OK;
     const int kpad = next_pow2(k_out);
-    const size_t smem = static_cast<size_t>(kpad) * sizeof(uint64_t);
+    const size_t smem = static_cast<size_t>(kpad + (R * k_in <= kRankSortMax ? R * k_in : 0)) * sizeof(uint64_t);
     SKY_CUDA(cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     if (stride_s <= 0) stride_s = static_cast<int64_t>(Q) * k_in;
     if (stride_i <= 0) stride_i = static_cast<int64_t>(Q) * k_in;

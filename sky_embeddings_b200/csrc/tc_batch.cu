@@ -446,7 +446,10 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
     }
     __syncthreads();
     bool done = false;
-    if (np <= kMpPool) {
+    if (np <= kRankSortMax) {
+        block_rank_topk(pool, np, k, kpad, sel);
+        done = true;
+    } else if (np <= kMpPool) {
         block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch);
         done = true;
     } else {
@@ -472,7 +475,10 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
                 }
             }
             __syncthreads();
-            if (nkeep <= kMpSample) {
+            if (nkeep <= kRankSortMax) {
+                block_rank_topk(extra, static_cast<int>(nkeep), k, kpad, sel);
+                done = true;
+            } else if (nkeep <= kMpSample) {
                 block_select_sort([&](int j) { return extra[j]; }, static_cast<int>(nkeep), k, kpad, sel, hist, scratch);
                 done = true;
             }

@@ -348,4 +348,26 @@ __device__ void block_select_sort(Fetch fetch, int n, int k, int kpad, uint64_t*
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Block-level exact top-k for SMALL candidate sets held in shared memory (n <= ~1024): every thread ranks
+// its candidates by counting the larger ones (all threads read the same element -> broadcast, no bank
+// conflicts) and drops them at sel[rank].  No radix passes, two barriers instead of ~80: this is the common
+// case of every merge once bounds exist (k plus a few hundred survivors).  Composites are distinct (0 = empty).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRankSortMax = 1024;
+__device__ __forceinline__ void block_rank_topk(const uint64_t* cand, int n, int k, int kpad, uint64_t* sel) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = tid; j < kpad; j += nt) sel[j] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const uint64_t v = cand[i];
+        if (v == 0) continue;
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) rank += (cand[j] > v) ? 1 : 0;
+        if (rank < k) sel[rank] = v;
+    }
+    __syncthreads();
+}
+
 }  // namespace sky
