@@ -237,14 +237,38 @@ def pixel_cases(ref):
     return out
 
 
+def c1_cases(ref):
+    """BASELINE config 1: similarity_search.py's call (similarity_search.py:169-171) with a random-init mim_1-shaped
+    encoder (tests/stub_encoder.StubViT: timm is absent), 1k target cutouts, 10k bank cutouts, cosine, top-10, CPU."""
+    from tests.stub_encoder import CutoutLoader, StubViT, c1_inputs
+    out = {}
+    bank, tgt, anchors = c1_inputs()
+    model = StubViT(seed=0)
+    with torch.no_grad():
+        target_latent = torch.cat([model.forward_features(torch.from_numpy(tgt[s:s + 100]))[0] for s in range(0, len(tgt), 100)])
+    out["checksum"] = np.array(checksum(bank[:64], tgt[:8]))
+    out["anchors"] = anchors
+    for mp, name in ((True, "maxpool"), (False, "patches")):
+        res = quiet(ref.mae_simsearch, model, target_latent, CutoutLoader(bank, 64), "cpu", metric="cosine", combine="min",
+                    use_weights=True, max_pool=mp, cls_token=False, nested_batches=False, n_save=10)
+        out[f"scores.{name}"] = res[3].numpy()
+        out[f"idx.{name}"] = res[2][:, 0].numpy().astype(np.int64)
+    return out
+
+
 def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(1)   # deterministic reduction order for the fixtures
+    only = sys.argv[1:]
     for name, fn in (("simsearch_small", simsearch_cases), ("simsearch_mim1_shape", mim1_shape_case),
                      ("short_bank", short_bank_case), ("compute_similarity", compute_similarity_cases),
-                     ("update_best", update_best_cases), ("pixel_small", pixel_cases)):
+                     ("update_best", update_best_cases), ("pixel_small", pixel_cases), ("c1_mim1_stub", c1_cases)):
+        if only and name not in only:
+            continue
+        if name == "c1_mim1_stub":
+            torch.set_num_threads(os.cpu_count() or 1)      # the encoder pass over 11k cutouts
         data = fn(ref)
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **data)

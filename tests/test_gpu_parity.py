@@ -683,3 +683,43 @@ def test_feeder_resident_bank_matches_reference_goldens(dev):
         assert np.array_equal(bs_.numpy(), bank_lat[idx.cpu().numpy()])
     for bank, _, _ in banks.values():
         bank.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 1: the reference driver's call with a random-init mim_1-shaped encoder
+# ------------------------------------------------------------------------------------------------
+def test_c1_mim1_stub_end_to_end(dev):
+    """similarity_search.py:169-171 through the drop-in mae_simsearch: stub ViT on the GPU, 1k target cutouts,
+    10k bank cutouts, cosine / min / use_weights=True, top-10 -- against the output of the reference's own
+    mae_simsearch for the same model and data (tests/golden/c1_mim1_stub.npz); then the resident-bank route
+    (feeder + one search) in fp32 and bf16."""
+    from sky_embeddings_b200 import bank_from_loader, resident_simsearch
+    from sky_embeddings_b200 import similarity as S
+    from tests.stub_encoder import CutoutLoader, StubViT, c1_inputs
+    g = G.load("c1_mim1_stub")
+    bank, tgt, anchors = c1_inputs()
+    assert G.checksum(bank[:64], tgt[:8]) == str(g["checksum"])
+    model = StubViT(seed=0).to(dev)
+    with torch.no_grad():
+        target_latent = torch.cat([model.forward_features(torch.from_numpy(tgt[s:s + 250]).to(dev))[0] for s in range(0, len(tgt), 250)])
+    for mp, name in ((True, "maxpool"), (False, "patches")):
+        smp, lat, ra, sc = S.mae_simsearch(model, target_latent, CutoutLoader(bank, 64), dev, metric="cosine", combine="min",
+                                           use_weights=True, max_pool=mp, cls_token=False, nested_batches=False, n_save=10)
+        idx = ra[:, 0].cpu().numpy().astype(np.int64)
+        # the encoder runs in fp32 on both sides but on different hardware: cosine scores agree to ~1e-6 absolute
+        ok, msg = O.check_topk_parity(sc.cpu().numpy(), idx, g[f"scores.{name}"], g[f"idx.{name}"], REL_F32, scale=1.0)
+        assert ok, f"mae_simsearch {name}: {msg}"
+        assert np.array_equal(smp.cpu().numpy(), bank[idx]) and lat.shape == (10, 65, 768)
+        for dtype, rel in (("fp32", REL_F32), ("bf16", REL_BF16)):
+            rb, rra, _ = bank_from_loader(model, CutoutLoader(bank, 64), dev, max_pool=mp, bank_dtype=dtype, n_items=len(bank))
+            _, ridx, _, rsc = resident_simsearch(rb, target_latent, rra, None, 1, 10, "cosine", "min", True, mp, False)
+            if dtype == "fp32":
+                ok, msg = O.check_topk_parity(rsc.cpu().numpy(), ridx.cpu().numpy(), g[f"scores.{name}"], g[f"idx.{name}"], rel, scale=1.0)
+                assert ok, f"resident {dtype} {name}: {msg}"
+            else:   # bf16 bank vs the fp32 reference: scores within 1e-3, the two planted anchors on top
+                assert set(ridx[:2].cpu().tolist()) == set(anchors.tolist())
+                ref = dict(zip(g[f"idx.{name}"].tolist(), g[f"scores.{name}"].tolist()))
+                for i_, s_ in zip(ridx.cpu().tolist(), rsc.cpu().tolist()):
+                    if i_ in ref:
+                        assert abs(s_ - ref[i_]) <= rel * max(abs(ref[i_]), 1.0), (name, i_, s_, ref[i_])
+            rb.close()
