@@ -201,8 +201,10 @@ def run_reference(args, wl):
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "bank_vectors": n_bank * world, "dim": D, "queries": Q, "k": k,
-                       "similarity": metric},
+            "config": {"workload": f"{args.workload}: {n_bank}-vector x {D} bf16 bank per GPU ({n_bank * world} total), "
+                                   f"{Q} queries, {metric} top-{k}, exact",
+                       "bank_vectors_per_gpu": n_bank, "bank_vectors": n_bank * world, "dim": D, "queries": Q, "k": k,
+                       "similarity": metric, "note": "reference algorithm on host cores (fp32), bounded sample scaled linearly"},
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
