@@ -58,8 +58,13 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     // every composite with key >= tau must be kept; tau == 0 / disabled keeps everything valid
     const uint64_t keep_ge = (use_gtau && tau_s != 0u) ? (static_cast<uint64_t>(tau_s) << 32) : 1ull;
 
+    // all list fills first (one L2 round trip instead of one per list), then the filtered gather
+    constexpr int kCountCache = 2048;
+    __shared__ int s_n[kCountCache];
+    for (int p = tid; p < P && p < kCountCache; p += kMergeThreads) s_n[p] = counts[static_cast<size_t>(p) * Qtot + q];
+    __syncthreads();
     for (int p = warp; p < P; p += nwarps) {
-        const int n = counts[static_cast<size_t>(p) * Qtot + q];
+        const int n = p < kCountCache ? s_n[p] : counts[static_cast<size_t>(p) * Qtot + q];
         const uint64_t* e = lists + (static_cast<size_t>(p) * Qtot + q) * cap;
         for (int i = lane; i < n; i += 32) {
             const uint64_t v = e[i];

@@ -461,9 +461,20 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
         }
         if (!emit) {
             ptx::named_bar_sync(1, kStConsumers);
-            if (tid < p.nq) {
-                p.counts[static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + tid] = sCnt[tid];
-                if (p.use_gtau && sLmax[tid]) st_cg_u32(p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + tid, sLmax[tid]);
+            if (tid < p.nq && p.use_gtau && sLmax[tid])
+                st_cg_u32(p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + tid, sLmax[tid]);
+            ptx::named_bar_sync(1, kStConsumers);
+            // Shrink this CTA's lists before handing them to the merge: the first row blocks went in unfiltered (no
+            // bound existed yet); what is below the grid-wide bound known NOW can never be in the top-k.  One warp
+            // per query compacts in place, so the merge kernel reads a handful of entries per CTA instead of hundreds.
+            if (warp < p.nq) {
+                const int q = warp;
+                int n = sCnt[q];
+                if (p.use_gtau) {
+                    const uint32_t lo = exchange_reduce(p.gtop + p.q0 + q, p.p_stride, p.Qtot, p.k);
+                    if (lo != 0u) n = warp_compact_ge(sink.lists + static_cast<size_t>(q) * p.cap, n, static_cast<uint64_t>(lo) << 32);
+                }
+                if (lane == 0) p.counts[static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q] = n;
             }
         }
     }
