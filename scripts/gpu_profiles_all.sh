@@ -12,7 +12,9 @@ line c2 --steps 200 --warmup 10
 line q1_fp32_weighted --workload q1 --bank-dtype fp32 --weighted --steps 50 --warmup 5 --no-cpu
 line q1_bf16 --workload q1 --steps 50 --warmup 5 --no-cpu
 line l64_fp32_weighted --workload l64 --bank-dtype fp32 --weighted --steps 50 --warmup 5 --no-cpu
+line c2_weighted --weighted --steps 100 --warmup 5 --no-cpu
 line c3 --workload c3 --steps 5 --warmup 3 --no-cpu
+line c3_shard_of_8 --workload c3g8 --steps 5 --warmup 3 --no-cpu
 line c4share --workload c4 --steps 5 --warmup 3 --no-cpu
 line c5_q1 --workload c5q1 --steps 5 --warmup 3
 line c5_q4 --workload c5 --steps 5 --warmup 3 --no-cpu
@@ -28,6 +30,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:
 echo "list rc=$?"
 prof c2_tc_search tc_search 5 $A
 prof q1_stream stream_search 3 --workload q1 --bank-dtype fp32 --weighted $A
-prof c3s_tc_batch tc_batch 9 --workload c3s --steps 1 --warmup 3 --no-cpu
+prof c3_tc_batch tc_batch 26 --workload c3 --steps 1 --warmup 3 --no-cpu
+prof c2w_tc_weighted tc_weighted 3 --weighted $A
 prof c5_pixel pixel_search 2 --workload c5s --steps 2 --warmup 3 --no-cpu
 ls -la $O
