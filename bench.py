@@ -36,6 +36,7 @@ WORKLOADS = {
     "c2": (1_000_000, 768, 64, 100, "cosine"),
     "c2mse": (1_000_000, 768, 64, 100, "MSE"),
     "small": (100_000, 768, 64, 100, "cosine"),
+    "mid": (100_000, 768, 512, 100, "cosine"),
     # the reference's own regime: one query (Q=1), and the widest single SIMT pass (Q=4)
     "q1": (1_000_000, 768, 1, 100, "cosine"),
     "q4": (1_000_000, 768, 4, 100, "cosine"),

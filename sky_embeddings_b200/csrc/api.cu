@@ -367,8 +367,20 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
     const bool batch_ok = tc_batch_supported(b, metric, w != nullptr, n_top_sims, k);
     if (path == SKY_PATH_BATCH && !batch_ok)
         return set_error(SKY_ERR_UNSUPPORTED, "batched tensor path needs a finalized bf16 bank, L=1, cosine/MSE, no weights, k <= 4096");
-    if (batch_ok && (path == SKY_PATH_BATCH || (path == SKY_PATH_AUTO && Q > 128)))
-        return launch_tc_batch(b, t, Q, metric, k, idx_offset, out_scores, out_idx, st);
+    bool use_batch = batch_ok && path == SKY_PATH_BATCH;
+    if (batch_ok && path == SKY_PATH_AUTO && Q > 128) {
+        // K2 streams the bank once per 64 queries (HBM bound); K2b is tensor bound but pays a launch + merge per
+        // phase.  Pick by a two-line cost model (constants from the measurements in DESIGN.md section 5).
+        const double bank_bytes = static_cast<double>(b->rows) * b->Dp * 2.0;
+        const double t_stream = ((Q + 63) / 64) * (bank_bytes / 6.0e12 + 40e-6) + 50e-6;
+        const int64_t tiles = (b->rows + kTileRows - 1) / kTileRows;
+        int phases = 0;
+        for (int64_t done = 0, per = 1; done * b->num_sms < tiles; ++phases) { done += per; if (phases >= 1) per *= 4; }
+        const double t_batch = 2.0 * Q * static_cast<double>(b->rows) * b->Dp / 1.1e15 + phases * 0.1e-3 + 0.1e-3;
+        // measured: 100k x 768, Q = 512: K2 0.51 ms, K2b 0.41 ms; 1M, Q = 4096: K2 19.0 ms, K2b 7.6 ms
+        use_batch = t_batch < t_stream;
+    }
+    if (use_batch) return launch_tc_batch(b, t, Q, metric, k, idx_offset, out_scores, out_idx, st);
 
     SearchState s;
     int rc;

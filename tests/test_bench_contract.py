@@ -1,0 +1,29 @@
+"""CPU: the bench.py contract that needs no GPU -- the reference arm prints one well-formed JSON line."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert d["metric"] == "queries/sec exact top-k over N-vector bank"
+    assert d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
