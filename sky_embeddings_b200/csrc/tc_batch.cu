@@ -412,8 +412,7 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
     if (tid == 0) npool = 0;
     __syncthreads();
     uint64_t* cq = carry + static_cast<size_t>(q) * kpad;
-    const uint64_t keep_gt = tauc[q];      // list entries were admitted with comp > tauc: all of them count
-    (void)keep_gt;
+    // list entries were admitted with comp > tauc[q]: every one of them counts
     for (int j = tid; j < k; j += kMpThreads) {
         const uint64_t v = cq[j];
         if (v) { const uint32_t pos = atomicAdd(&npool, 1u); if (pos < kMpPool) pool[pos] = v; }

@@ -160,6 +160,40 @@ class Bank:
             bank.upload(latents[s:s + chunk_items], s, token_mode, num_extra_tokens)
         return bank.finalize()
 
+    # -- persisted bank cache --------------------------------------------------------------------
+    def save(self, path, chunk_items=1 << 18):
+        """Persist the resident bank (stored, normalised rows + the first-batch statistics) so that later runs
+        skip the encoder and the ingest statistics: the reference re-encodes the whole bank for every target
+        (utils/similarity.py:71-102).  bf16 banks are written as their 16-bit patterns (exact)."""
+        import numpy as np
+        rows = np.empty((self.n_items, self.L, self.D), dtype=np.uint16 if self.dtype == L.BF16 else np.float32)
+        for s0 in range(0, self.n_items, chunk_items):
+            x = self.download(s0, min(chunk_items, self.n_items - s0))
+            if self.dtype == L.BF16:
+                rows[s0:s0 + x.shape[0]] = x.to(torch.bfloat16).view(torch.int16).cpu().numpy().view(np.uint16)
+            else:
+                rows[s0:s0 + x.shape[0]] = x.cpu().numpy()
+        mu, sigma = (t.cpu().numpy() for t in self.norm()) if self.has_norm else (np.zeros(0, np.float32),) * 2
+        np.savez(path, rows=rows, mu=mu, sigma=sigma, meta=np.array([self.n_items, self.L, self.D, self.dtype], dtype=np.int64))
+
+    @classmethod
+    def load(cls, path, device=None, chunk_items=1 << 18):
+        """Rebuild a bank saved with save(): rows are uploaded as stored (no re-normalisation), then the saved
+        statistics are attached so that query_from_targets normalises target groups exactly as before."""
+        import numpy as np
+        z = np.load(path)
+        n, Lt, D, dt = (int(v) for v in z["meta"])
+        bank = cls(n, Lt, D, "bf16" if dt == L.BF16 else "fp32", device)
+        rows = z["rows"]
+        for s0 in range(0, n, chunk_items):
+            part = torch.from_numpy(np.ascontiguousarray(rows[s0:s0 + chunk_items]))
+            if dt == L.BF16:
+                part = part.view(torch.int16).view(torch.bfloat16)
+            bank.upload(part, s0, "all", 0)
+        if z["mu"].size:
+            bank.set_norm(torch.from_numpy(z["mu"]), torch.from_numpy(z["sigma"]))
+        return bank.finalize()
+
     # -- queries ----------------------------------------------------------------------------
     def query_from_targets(self, targets, use_weights=True):
         """determine_target_features (utils/similarity.py:134-147) on the normalised target group.

@@ -723,3 +723,26 @@ def test_c1_mim1_stub_end_to_end(dev):
                     if i_ in ref:
                         assert abs(s_ - ref[i_]) <= rel * max(abs(ref[i_]), 1.0), (name, i_, s_, ref[i_])
             rb.close()
+
+
+def test_bank_save_load_round_trip(dev, tmp_path):
+    """Persisted bank cache: a reloaded bank stores the same bits, normalises targets
+    the same way and returns identical search results."""
+    from sky_embeddings_b200 import Bank, synth
+    lat = synth.latents(3000, 5, 96, stream=401)
+    tgt = synth.target_group(lat, [7, 1500], copies=5, noise=0.3, stream=402)
+    for dtype in ("bf16", "fp32"):
+        bank = Bank.from_latents(torch.from_numpy(lat).to(dev), norm_rows=64, token_mode="patches", num_extra_tokens=1, dtype=dtype)
+        tsel = torch.from_numpy(O.token_select(tgt, 1, False, False)).to(dev)
+        t, w = bank.query_from_targets(tsel)
+        s0, i0 = bank.search(t, w, k=20, metric="cosine", combine="min")
+        f = str(tmp_path / f"bank_{dtype}.npz")
+        bank.save(f)
+        again = Bank.load(f, dev)
+        assert torch.equal(again.download(), bank.download())
+        t2, w2 = again.query_from_targets(tsel)
+        assert torch.equal(t2, t) and torch.equal(w2, w)
+        s1, i1 = again.search(t2, w2, k=20, metric="cosine", combine="min")
+        assert torch.equal(i1, i0) and torch.equal(s1, s0)
+        bank.close()
+        again.close()
