@@ -159,9 +159,17 @@ def cpu_sample(D, k, metric, rows, n_queries, batch=512, seed=0):
     return time.perf_counter() - t0
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are to use every host core they can."""
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_baseline_block(n_bank, D, Q, k, metric, budget_s=15.0):
     import torch
-    cores = torch.get_num_threads()
+    cores = use_all_host_threads()
     rows = min(n_bank, 100_000)
     cpu_sample(D, k, metric, min(rows, 20_000), 1)            # warm-up
     t1 = cpu_sample(D, k, metric, rows, 1)
@@ -180,7 +188,7 @@ def run_reference(args, wl):
         return 0
     import torch
     n_bank, D, Q, k, metric = wl
-    cores = torch.get_num_threads()
+    cores = use_all_host_threads()
     # bounded sample: size one step so that the whole --steps/--warmup run ends within ~2 minutes
     nq = 1
     probe_rows = min(n_bank, 20_000)
