@@ -259,6 +259,12 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
         const int L = p.L;
         int stage = 0;
         uint32_t phase = 0;
+        // a list takes at most R (L = 1) or R / L inserts per row block; with cap well above k the CTA-wide
+        // barrier pair of the overflow check is only needed every few blocks
+        const int per_block = (L == 1) ? R : R / L;
+        int check_every = emit ? 1 : (p.cap - p.k) / (2 * per_block);
+        check_every = check_every < 1 ? 1 : (check_every > 16 ? 16 : check_every);
+        const int prune_slack = check_every * per_block;
 
         for (int i = 0; i < my_blocks; ++i) {
             const int64_t rb = rb_lo + blockIdx.x + static_cast<int64_t>(i) * gridDim.x;
@@ -450,12 +456,13 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
                 }
             }
             if (p.debug & 4) {
-            } else if (!emit) {
+            } else if (!emit && (i + 1) % check_every == 0) {
+                // overflow check, every check_every row blocks: at most prune_slack inserts per query in between
                 ptx::named_bar_sync(1, kStConsumers);
-                sink_prune_if_full(sink, p.nq, warp, kStWarps, smem_addr(sHist + warp * 256));
+                sink_prune_if_full(sink, p.nq, warp, kStWarps, smem_addr(sHist + warp * 256), prune_slack);
                 ptx::named_bar_sync(1, kStConsumers);
             } else if (L != 1) {
-                ptx::named_bar_sync(1, kStConsumers);
+                ptx::named_bar_sync(1, kStConsumers);       // token scores of this block are consumed
             }
             if (tid == 0) *sBlocksDone = i + 1;
         }

@@ -193,13 +193,14 @@ __device__ __forceinline__ void sink_prune(const Sink& s, int q, uint32_t hist) 
 }
 
 // Called by `nwarps` warps (warp_in_group = 0..nwarps-1) between two barriers.
+// slack: the most inserts per query that can happen before the next call (cap >= k + slack).
 __device__ __forceinline__ void sink_prune_if_full(const Sink& s, int nq, int warp_in_group, int nwarps,
-                                                   uint32_t hist) {
+                                                   uint32_t hist, int slack = kPruneSlack) {
     // one vector pass over the counts instead of a serial chain of dependent shared loads
     const int lane = threadIdx.x & 31;
     for (int base = 0; base < nq; base += 32 * nwarps) {
         const int q = base + lane * nwarps + warp_in_group;      // this warp owns q % nwarps == warp_in_group
-        const bool full = q < nq && static_cast<int>(lds_u32(s.cnt + q * 4)) > s.cap - kPruneSlack;
+        const bool full = q < nq && static_cast<int>(lds_u32(s.cnt + q * 4)) > s.cap - slack;
         uint32_t todo = __ballot_sync(0xffffffffu, full);
         while (todo) {
             const int l = __ffs(todo) - 1;
