@@ -8,7 +8,6 @@ import argparse
 import os
 import shutil
 import subprocess
-import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -13,7 +13,6 @@ CUDA device, otherwise the calls raise.
 """
 from __future__ import annotations
 
-import ctypes as C
 import time
 
 import torch
