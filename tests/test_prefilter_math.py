@@ -92,3 +92,20 @@ def test_weighted_cosine_prefilter_never_rejects_an_exact_pass():
     rhs = fma(-np.abs(rhs), np.full_like(rhs, F(8e-6)), rhs)
     pre_pass = ~((x * np.abs(x)).astype(F) < rhs)
     assert not np.any(exact_pass & ~pre_pass)
+
+
+def test_k2_cosine_prefilter_never_rejects_an_exact_pass():
+    """csrc/tc_search.cu epilogue: bound = th (|t||z| + 1e-6), lowered by 1e-6 relative; pass iff !(dot < bound)."""
+    rng, qq, rn, dot = _cases(2_000_000, 4)
+    qc, mx = np.sqrt(qq).astype(F), np.sqrt(rn).astype(F)
+    den = fma(qc, mx, np.full_like(qc, F(1e-6)))
+    sv = (dot / den).astype(F)
+    ulps = rng.integers(-3, 4, sv.shape[0])
+    th = sv.copy()
+    for _ in range(3):
+        th = np.where(ulps > 0, np.nextafter(th, F(np.inf)), np.where(ulps < 0, np.nextafter(th, F(-np.inf)), th)).astype(F)
+        ulps = ulps - np.sign(ulps)
+    exact_pass = sv >= th
+    bound = (th * den).astype(F)
+    bound = fma(-np.abs(bound), np.full_like(bound, F(1e-6)), bound)
+    assert not np.any(exact_pass & ~(~(dot < bound)))
