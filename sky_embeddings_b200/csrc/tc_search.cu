@@ -5,12 +5,13 @@
 //   cosine :163-170   s = t.z / (|t| |z| + 1e-6)            |z|^2 = row norm stored with the bank
 //   MSE    :188-192   s = (|t|^2 - 2 t.z + |z|^2) / D^2     (rank-equivalent to L2)
 // One persistent CTA per SM.  Warp roles:
-//   warp 0      TMA producer: the query matrix B[BN, Dp] once (resident in shared memory for the
-//               whole kernel), then 128-row x 64-col bank boxes through a ring of stages
-//   warp 1      MMA issuer (one thread): tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM,
-//               two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 2-5   epilogue: tcgen05.ld accumulators -> score -> threshold filter -> candidate sink
-//   warp 6      grid-wide threshold exchange (publishes / refreshes the top-k lower bound)
+//   warps 0-3   bank stream: 128 threads copy each contiguous 16 KB (tile, k-block) piece with 16-byte cp.async
+//               into the 128-byte-swizzled ring stage; thread 0 also loads the query matrix B[BN, Dp] once by
+//               TMA (resident in shared memory for the whole kernel)
+//   warps 4-7   epilogue: tcgen05.ld accumulators -> conservative pre-filter bitmask -> exact insert of survivors
+//   warp 8      MMA issuer (one thread): tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM, two accumulator
+//               stages so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warp 9      grid-wide threshold exchange (publishes / refreshes the top-k lower bound)
 // The bank streams from HBM exactly once per launch; no score ever goes to HBM.
 #include <cstdlib>
 
