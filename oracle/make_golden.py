@@ -30,48 +30,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sky_embeddings_b200 import synth  # noqa: E402
 
-REF = "/root/reference/utils/similarity.py"
 OUT = os.path.join(ROOT, "tests", "golden")
 
-
-def load_reference():
-    spec = importlib.util.spec_from_file_location("ref_similarity", REF)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
-
-
-class LatentStub:
-    """Stands in for the ViT: the 'images' it is fed are already latents."""
-
-    def __init__(self, num_extra_tokens=1):
-        self.num_extra_tokens = num_extra_tokens
-
-    def eval(self):
-        return self
-
-    def forward_features(self, samples, ra_dec=None, reshape_out=False):
-        return samples, None, None
-
-
-class LatentLoader:
-    """Flat loader over a latent bank: yields (latents[B,...], mask, ra_dec[B,2]);
-    ra_dec[:,0] = bank row (exact in f32 below 2**24), ra_dec[:,1] = 0."""
-
-    def __init__(self, bank, batch_size):
-        self.bank = torch.as_tensor(bank)
-        self.bs = batch_size
-
-    def __len__(self):
-        return (self.bank.shape[0] + self.bs - 1) // self.bs
-
-    def __iter__(self):
-        n = self.bank.shape[0]
-        for s in range(0, n, self.bs):
-            e = min(n, s + self.bs)
-            ra = torch.zeros((e - s, 2), dtype=torch.float32)
-            ra[:, 0] = torch.arange(s, e, dtype=torch.float32)
-            yield self.bank[s:e], torch.zeros(e - s), ra
+from oracle.ref_harness import LatentLoader, LatentStub, load_reference, quiet  # noqa: E402
 
 
 def checksum(*arrays):
@@ -79,11 +40,6 @@ def checksum(*arrays):
     for a in arrays:
         h.update(np.ascontiguousarray(a).tobytes())
     return h.hexdigest()[:16]
-
-
-def quiet(fn, *a, **kw):
-    with contextlib.redirect_stdout(io.StringIO()):
-        return fn(*a, **kw)
 
 
 def simsearch_cases(ref):

@@ -20,6 +20,12 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 void count_launch(int n) { g_launches += n; }
+#ifdef SKY_EXPERIMENTS
+int env_knob(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+#endif
 
 static int grow(void** p, size_t* have, size_t want) {
     if (*have >= want) return SKY_OK;
@@ -48,6 +54,8 @@ void prof_mark(const sky_bank* b, cudaStream_t st) {
     cudaEventRecord(e, st);
     b->prof_events->push_back(e);
 }
+
+constexpr int kAutoStreamMaxQ = 4;   // widest single pass of K1
 
 static bool valid_metric(int m) { return m == SKY_COSINE || m == SKY_MSE || m == SKY_MAE; }
 static bool valid_combine(int c) { return c == SKY_MEAN || c == SKY_MIN || c == SKY_MAX; }
@@ -261,7 +269,8 @@ int sky_bank_finalize(sky_bank_t* b, void* stream) {
     return SKY_OK;
 }
 
-/* debug only (not part of the public header): timeline of the tensor kernel, see tc_search.cu */
+#ifdef SKY_EXPERIMENTS
+/* experiment builds only (not part of the public header): kernel timelines, see tc_search.cu */
 __attribute__((visibility("default"))) int sky_debug_trace(unsigned long long* h_out, int n) { return debug_read_trace(h_out, n); }
 
 __attribute__((visibility("default"))) int sky_debug_stream_stats(unsigned long long* h_out, int reset) { return debug_stream_stats(h_out, reset); }
@@ -269,6 +278,7 @@ __attribute__((visibility("default"))) int sky_debug_stream_stats(unsigned long 
 __attribute__((visibility("default"))) int sky_debug_tb_trace(long long* h_out, int n) { return debug_read_tb_trace(h_out, n); }
 
 __attribute__((visibility("default"))) int sky_debug_epi(unsigned long long* h_out) { return debug_read_epi(h_out); }
+#endif
 
 int sky_profile_enable(sky_bank_t* b, int enable) {
     if (!b) return set_error(SKY_ERR_ARG, "bank is NULL");
@@ -327,6 +337,16 @@ int sky_query_from_targets(const sky_bank_t* b, const float* targets, int64_t T_
     if (T_rows < 1 || D < 1) return set_error(SKY_ERR_ARG, "bad target shape");
     if (b && b->D != D) return set_error(SKY_ERR_ARG, "target D=%d differs from bank D=%d", D, b->D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // without a bank the kernels run on the device that owns `targets`
+    int dev = b ? b->device : -1;
+    if (dev < 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, targets) != cudaSuccess || pa.type != cudaMemoryTypeDevice)
+            return set_error(SKY_ERR_ARG, "targets is not a device pointer (there is no CPU fallback)");
+        dev = pa.device;
+    }
+    DeviceGuard g(dev);
+    if (!g.ok) return set_error(SKY_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
     const bool nrm = b && b->has_norm;
     // std goes to w_out first, then is turned into weights in place
     int rc = launch_col_stats(targets, T_rows, D, D, 0, nrm ? b->mu : nullptr, nrm ? b->sp : nullptr, t_out, w_out, st);
@@ -348,8 +368,11 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
     const bool tw_ok = tc_weighted_supported(b, metric, w != nullptr, n_top_sims);
     if (path == SKY_PATH_TENSOR && !tc_ok && !tw_ok)
         return set_error(SKY_ERR_UNSUPPORTED, "tensor path needs a bf16 bank, L=1, cosine/MSE, no n_top_sims");
-    if (tw_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q >= 2))) {
-        SearchState sw;
+    // AUTO keeps Q <= kAutoStreamMaxQ on the streaming kernel K1 (one bank pass, fp32 queries): the tensor paths
+    // round the query operands to bf16, and the reference's own regime (one query, or a handful) must not score
+    // differently depending on the batch size
+    if (tw_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q > kAutoStreamMaxQ))) {
+        SearchState sw{};
         const int grid = tc_grid(b);
         int rcw = plan_state(b, grid, Q, k, grid, &sw);
         if (rcw) return rcw;
@@ -362,7 +385,7 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
         return launch_merge_lists(sw, metric, idx_offset, out_scores, out_idx, st);
     }
     // small query batches stay on the streaming SIMT kernel (HBM bound there); larger ones need MMA
-    const bool use_tc = tc_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q >= 2));
+    const bool use_tc = tc_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q > kAutoStreamMaxQ));
     // large query batches: the GEMM-shaped kernel (bank tile reused by all query groups through L2)
     const bool batch_ok = tc_batch_supported(b, metric, w != nullptr, n_top_sims, k);
     if (path == SKY_PATH_BATCH && !batch_ok)
@@ -382,7 +405,7 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
     }
     if (use_batch) return launch_tc_batch(b, t, Q, metric, k, idx_offset, out_scores, out_idx, st);
 
-    SearchState s;
+    SearchState s{};
     int rc;
     if (use_tc) {
         const int grid = tc_grid(b);
@@ -482,10 +505,9 @@ int sky_score(sky_bank_t* b, const float* t, const float* w, int Q, int metric, 
     a.dtype = b->dtype; a.n_items = n_items; a.L = b->L; a.D = b->D; a.Dp = b->Dp;
     a.t = t; a.w = w; a.Q = Q; a.metric = metric; a.combine = combine; a.n_top = n_top_sims;
     a.emit = out_scores; a.item0 = 0; a.n = n_items;
-    SearchState s;   // unused in emit mode
+    SearchState s{};   // unused in emit mode
     const int sqc = stream_pick_qc(Q);
-    static const char* force_generic = getenv("SKY_SCORE_GENERIC");
-    if (!force_generic && stream_supported(b, sqc))
+    if (!env_knob("SKY_SCORE_GENERIC", 0) && stream_supported(b, sqc))
         return launch_stream_search(b, a, s, stream_grid(b, a.row0, a.row0 + n_items * b->L), sqc, st);
     const int qc = (Q == 1) ? 1 : simt_pick_qc(b->Dp);
     int grid = 1;
@@ -553,7 +575,7 @@ static int pixel_impl(sky_bank_t* b, const float* q, const unsigned char* qmask,
     rc = launch_pixel_fold(q, qmask, nq, qp, st);
     if (rc) return rc;
     const int qc = pixel_pick_qc(Q);
-    SearchState s;
+    SearchState s{};
     if (emit) {
         if (n_items == 0) return SKY_OK;
         return launch_pixel_search(b, qp, Q, item0, item0 + n_items, s, pixel_grid(b, n_items), qc, emit, st);

@@ -110,9 +110,8 @@ __global__ void add_eps_kernel(const float* __restrict__ sigma, float* __restric
 }
 
 // w = 1/std^2, normalised to sum 1 (utils/similarity.py:143-145); ones if !use_weights (:246-247).
-// Single block.
-__global__ void finish_weights_kernel(const float* __restrict__ std_in, int D, int use_weights,
-                                      float* __restrict__ w_out) {
+// Single block.  std_in may alias w_out (in-place use by sky_query_from_targets): no __restrict__ here.
+__global__ void finish_weights_kernel(const float* std_in, int D, int use_weights, float* w_out) {
     __shared__ double red[32];
     double s = 0.0;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {

@@ -77,6 +77,20 @@ __host__ __device__ __forceinline__ size_t tile_offset(int64_t row, int d, int k
 }
 
 // ---------------------------------------------------------------------------------------------
+// Experiment knobs (SKY_*_DEBUG / _STAGES / _POLICY ... environment variables, kernel timelines).  They exist only
+// in a build made with SKY_NVCC_DEFS=-DSKY_EXPERIMENTS: the release library never reads the environment, so a stray
+// variable cannot change a result (several of the debug bits skip parts of the math), and the debug branches and
+// trace buffers are compiled out of the kernels.
+// ---------------------------------------------------------------------------------------------
+#ifdef SKY_EXPERIMENTS
+#define SKY_DBG(p) ((p).debug)
+int env_knob(const char* name, int dflt);     // api.cu
+#else
+#define SKY_DBG(p) 0
+static inline int env_knob(const char*, int dflt) { return dflt; }
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // host-side error plumbing (api.cu owns the storage)
 // ---------------------------------------------------------------------------------------------
 int set_error(int code, const char* fmt, ...);

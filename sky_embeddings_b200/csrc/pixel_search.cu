@@ -274,8 +274,8 @@ static size_t px_fixed_bytes(int qc) {
 }
 
 int pixel_pick_qc(int Q) {
-    static const char* e = getenv("SKY_PX_QC");      // experiments
-    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) return atoi(e);
+    const int e = env_knob("SKY_PX_QC", 0);      // experiments
+    if (e == 1 || e == 2 || e == 4) return e;
     return Q == 1 ? 1 : (Q == 2 ? 2 : 4);
 }
 
@@ -303,7 +303,7 @@ static int pixel_launch_one(const PixelParams& p, int grid, size_t smem, cudaStr
 int launch_pixel_search(const sky_bank* b, const float* qp, int Q, int64_t row_lo, int64_t row_hi, const SearchState& s,
                         int grid, int qc, float* emit, cudaStream_t st) {
     int stages = kPxMaxStages;
-    { static const char* e = getenv("SKY_PX_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
+    { const int e = env_knob("SKY_PX_STAGES", 0); if (e >= 2 && e < stages) stages = e; }
     const size_t smem = static_cast<size_t>(stages) * kPxChunk + px_fixed_bytes(qc);
     for (int q0 = 0; q0 < Q; q0 += qc) {
         PixelParams p;

@@ -53,7 +53,9 @@ struct StreamParams {
     float* emit; int64_t emit_item0; int64_t emit_n;
 };
 
+#ifdef SKY_EXPERIMENTS
 __device__ unsigned long long g_st_stats[8];   // debug (SKY_ST_DEBUG bit 4): [0] inserts tried, [1] passed exact test, [2] prunes
+#endif
 
 // ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ------------------
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
                     if (lane == 0) exchange_apply(sink, q, lo);
                 }
                 ++round;
-                __nanosleep((p.debug & 128) ? 4000 : (round < 32 ? 200 : 4000));
+                __nanosleep((SKY_DBG(p) & 128) ? 4000 : (round < 32 ? 200 : 4000));
             }
         }
     } else if (warp < kStWarps) {
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
                 if (p.spin) ptx::mbar_wait(&full_bar[stage], phase);
                 else ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);
                 const uint32_t src = stage0 + static_cast<uint32_t>(stage) * kStChunk + my_off;
-                if (p.debug & 1) {
+                if (SKY_DBG(p) & 1) {
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
                     if (++stage == S) { stage = 0; phase ^= 1; }
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
 
-            if (p.debug & 2) { if (tid == 0) *sBlocksDone = i + 1; continue; }
+            if (SKY_DBG(p) & 2) { if (tid == 0) *sBlocksDone = i + 1; continue; }
             // ---- row sums: fold the pair, then across the LPR lanes that share a row ---------------
             float mine[NRG];     // score of (row group rg, row lr, query lc) on lanes with lc < QC
             const float qc = sQc[lc < QC ? lc : 0];
@@ -392,15 +394,17 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
                         if (emit) {
                             if (row >= p.emit_item0 && row < p.emit_item0 + p.emit_n)
                                 p.emit[static_cast<size_t>(p.q0 + lc) * p.emit_n + (row - p.emit_item0)] = mine[rg];
-                        } else if ((p.debug & 8) || ((p.debug & 32) && i >= 2) || ((p.debug & 64) && i < 2)) {
+                        } else if ((SKY_DBG(p) & 8) || ((SKY_DBG(p) & 32) && i >= 2) || ((SKY_DBG(p) & 64) && i < 2)) {
                             if (mine[rg] == 123.456f) p.counts[0] = 1;      // keep the score alive
                         } else if (largest ? !(mine[rg] < thrf) : !(mine[rg] > thrf)) {      // NaN passes
-                            if (p.debug & 16) {
+#ifdef SKY_EXPERIMENTS
+                            if (SKY_DBG(p) & 16) {
                                 atomicAdd(&g_st_stats[0], 1ull);
                                 if (make_composite(score_to_key(mine[rg], largest), static_cast<uint32_t>(row)) > sink_thr(sink, lc)) atomicAdd(&g_st_stats[1], 1ull);
                                 if (i < 8) atomicAdd(&g_st_stats[3], 1ull);
                                 if (i < 2) atomicAdd(&g_st_stats[4], 1ull);
                             }
+#endif
                             sink_insert_one(sink, lc, make_composite(score_to_key(mine[rg], largest), static_cast<uint32_t>(row)));
                         }
                     }
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
                     }
                 }
             }
-            if (p.debug & 4) {
+            if (SKY_DBG(p) & 4) {
             } else if (!emit && (i + 1) % check_every == 0) {
                 // overflow check, every check_every row blocks: at most prune_slack inserts per query in between
                 ptx::named_bar_sync(1, kStConsumers);
@@ -509,12 +513,14 @@ static int st_stages(int Dp, int qc, int R) {
     return static_cast<int>(s > kStMaxStages ? kStMaxStages : s);
 }
 
+#ifdef SKY_EXPERIMENTS
 int debug_stream_stats(unsigned long long* h_out, int reset) {
     SKY_CUDA(cudaDeviceSynchronize());
     SKY_CUDA(cudaMemcpyFromSymbol(h_out, g_st_stats, sizeof(g_st_stats)));
     if (reset) { unsigned long long z[8] = {0}; SKY_CUDA(cudaMemcpyToSymbol(g_st_stats, z, sizeof(z))); }
     return SKY_OK;
 }
+#endif
 
 int stream_pick_qc(int Q) { return Q == 1 ? 1 : 4; }
 
@@ -559,11 +565,11 @@ static int stream_launch_m(int metric, int qc, bool weighted, const StreamParams
 int launch_stream_search(const sky_bank* b, const SimtArgs& a, const SearchState& s, int grid, int qc, cudaStream_t st) {
     const int R = st_rows_per_block(a.dtype);
     int stages = st_stages(a.Dp, qc, R);
-    { static const char* e = getenv("SKY_ST_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
+    { const int e = env_knob("SKY_ST_STAGES", 0); if (e >= 2 && e < stages) stages = e; }
     int split = 1;
-    { static const char* e = getenv("SKY_ST_SPLIT"); if (e && atoi(e) >= 0 && atoi(e) <= 16) split = atoi(e); }
+    { const int e = env_knob("SKY_ST_SPLIT", -1); if (e >= 0 && e <= 16) split = e; }
     unsigned long long policy = ptx::kEvictFirst;
-    { static const char* e = getenv("SKY_ST_POLICY"); const int pv = e ? atoi(e) : 0;
+    { const int pv = env_knob("SKY_ST_POLICY", 0);
       policy = pv == 1 ? 0x1000000000000000ull : (pv == 2 ? ptx::kEvictLast : ptx::kEvictFirst); }
     if (stages < 2) return set_error(SKY_ERR_UNSUPPORTED, "streaming scorer: D=%d does not fit in shared memory", a.Dp);
     const size_t smem = static_cast<size_t>(stages) * kStChunk + st_fixed_bytes(a.Dp, qc, R);
@@ -577,8 +583,8 @@ int launch_stream_search(const sky_bank* b, const SimtArgs& a, const SearchState
         p.combine = a.combine; p.n_top = a.n_top;
         p.stages = stages;
         p.split = split;
-        { static const char* e = getenv("SKY_ST_SPIN"); p.spin = e ? atoi(e) : 0; }
-        { static const char* e = getenv("SKY_ST_DEBUG"); p.debug = e ? atoi(e) : 0; }
+        p.spin = env_knob("SKY_ST_SPIN", 0);
+        p.debug = env_knob("SKY_ST_DEBUG", 0);
         p.policy = policy;
         p.lists = s.lists; p.counts = s.counts; p.gtop = s.gtop;
         p.p_stride = s.p_stride; p.Qtot = s.Qtot; p.cap = s.cap; p.k = s.k; p.use_gtau = s.use_gtau;

@@ -64,9 +64,13 @@ __device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
 
 // debug timeline (SKY_TB_DEBUG bit 5 = 32): clock64 stamps of CTA 0, epilogue warp e = 0, per visit of the launch:
 // [0] visit start, [1] accumulator ready, [2] chunks done, [3] write-back done, [4] = 1 if anything was inserted
+#ifdef SKY_EXPERIMENTS
 constexpr int kTbTrace = 4096;
 __device__ long long g_tb_trace[kTbTrace * 4 * 5];
-#define TB_TRACE(slot, val) do { if ((p.debug & 32) && blockIdx.x == 0 && lane == 0 && v < kTbTrace) g_tb_trace[(v * 4 + e) * 5 + (slot)] = (val); } while (0)
+#define TB_TRACE(slot, val) do { if ((SKY_DBG(p) & 32) && blockIdx.x == 0 && lane == 0 && v < kTbTrace) g_tb_trace[(v * 4 + e) * 5 + (slot)] = (val); } while (0)
+#else
+#define TB_TRACE(slot, val) do { } while (0)
+#endif
 
 // tcgen05.wait::ld that also "touches" the destination registers of an earlier tcgen05.ld, so that the compiler
 // cannot move their first use above the wait when other work sits between the load and the wait
@@ -161,7 +165,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     for (int k = 0; k < kKBlock / 16; ++k) {
                         const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_addr + k * 32);
                         const uint64_t b_desc = ptx::make_sw128_kmajor_desc(b_addr + k * 32);
-                        if (!(p.debug & 2)) ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(SKY_DBG(p) & 2)) ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == kTbStages) { stage = 0; phase ^= 1; }
@@ -267,7 +271,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         mbits |= (!(dot < bound) ? 1u : 0u) << (i * 4 + u);       // NaN passes
                     }
                 }
-                if (p.debug & 4) mbits = 0;
+                if (SKY_DBG(p) & 4) mbits = 0;
                 mbits = valid ? mbits : 0u;
                 // EXACT PATH (rare once bounds exist): every lane walks its own survivors -- the warp runs as many
                 // rounds as its busiest lane has bits; columns beyond the real queries carry a +inf bound and never pass
@@ -291,7 +295,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const float qcv = sQc[qi];
                     const float sv = largest ? dot / fmaf(qcv, mx, 1e-6f) : (qcv - 2.0f * dot + rn) * p.inv_dd;
                     const uint64_t comp = make_composite(score_to_key(sv, largest), static_cast<uint32_t>(row));
-                    if (comp > sTau[qi] && !(p.debug & 16)) {
+                    if (comp > sTau[qi] && !(SKY_DBG(p) & 16)) {
                         // cap >= k + 256 and at most 128 rows per visit: the list cannot overflow before the check below
                         const uint32_t pos = atoms_add_u32(smem_addr(&sCnt[qi]), 1u);
                         st_cg_u64(my_lists + static_cast<size_t>(q) * p.cap + pos, comp);
@@ -306,7 +310,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             for (int c2 = 0; c2 < kTbBN / 64; ++c2) {
                 tmem_ld_wait_touch(va);
                 ptx::tmem_ld_32x32b_x32(taddr + (2 * c2 + 1) * 32, vb);
-                if (!(p.debug & 1)) process(va, 2 * c2);
+                if (!(SKY_DBG(p) & 1)) process(va, 2 * c2);
                 tmem_ld_wait_touch(vb);
                 if (c2 + 1 < kTbBN / 64) {
                     ptx::tmem_ld_32x32b_x32(taddr + (2 * c2 + 2) * 32, va);
@@ -315,7 +319,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
                 }
-                if (!(p.debug & 1)) process(vb, 2 * c2 + 1);
+                if (!(SKY_DBG(p) & 1)) process(vb, 2 * c2 + 1);
             }
             TB_TRACE(2, clock64());
             TB_TRACE(4, inserted ? 1 : 0);
@@ -324,7 +328,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (p.dense) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) st_cg_i32(my_counts + g * kTbBN + et + j * 128, kTileRows);
-            } else if (!(p.debug & 8) && named_bar_or(3, kTbEpiThreads, inserted)) {
+            } else if (!(SKY_DBG(p) & 8) && named_bar_or(3, kTbEpiThreads, inserted)) {
                 // warp e owns queries [64 e, 64 e + 64) of the group; lane handles two of them
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -523,12 +527,14 @@ __global__ void batch_init_kernel(uint64_t* carry, uint64_t* tauc, int* counts, 
 int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows);                 // tc_search.cu
 int launch_pack_queries(const float* t, int Q, int D, int Dp, int q_pad, int metric, void* bq, float* qconst, cudaStream_t st);
 
+#ifdef SKY_EXPERIMENTS
 int debug_read_tb_trace(long long* h_out, int n) {
     if (n > kTbTrace * 20) n = kTbTrace * 20;
     SKY_CUDA(cudaDeviceSynchronize());
     SKY_CUDA(cudaMemcpyFromSymbol(h_out, g_tb_trace, sizeof(long long) * n));
     return SKY_OK;
 }
+#endif
 
 static int tb_next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
@@ -593,7 +599,7 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     p.lists = lists; p.counts = counts;
     p.Qp = Qp; p.nq = Q; p.cap = cap; p.k = k; p.groups = G; p.metric = metric; p.kblocks = KB;
     p.rows = b->rows;
-    { static const char* e = getenv("SKY_TB_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    p.debug = env_knob("SKY_TB_DEBUG", 0);
     p.inv_dd = 1.0f / (static_cast<float>(b->D) * static_cast<float>(b->D));
     const float dd = static_cast<float>(b->D) * static_cast<float>(b->D);
 
@@ -602,8 +608,8 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     int per_cta = 1;
     bool first = true;
     int growth = 4;       // phase sizes 1, 1, 4, 16, ... tiles per CTA: fewer merges, a few more survivors per phase
-    { static const char* e = getenv("SKY_TB_PHASE0"); if (e && atoi(e) >= 1) per_cta = atoi(e); }
-    { static const char* e = getenv("SKY_TB_GROWTH"); if (e && atoi(e) >= 2) growth = atoi(e); }
+    { const int e = env_knob("SKY_TB_PHASE0", 0); if (e >= 1) per_cta = e; }
+    { const int e = env_knob("SKY_TB_GROWTH", 0); if (e >= 2) growth = e; }
     while (t0 < num_tiles) {
         int t1 = t0 + per_cta * P;
         if (t1 > num_tiles || num_tiles - t1 < P) t1 = num_tiles;      // fold a short tail into this phase

@@ -56,11 +56,16 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 
 // debug timeline (SKY_TC_DEBUG bit 3): clock64 stamps of CTA 0, rows: 0 producer issue, 1 MMA saw full,
 // 2 MMA committed, 3 epilogue saw tmem_full, 4 epilogue tile done
+#ifdef SKY_EXPERIMENTS
 constexpr int kTraceLen = 1024;
 __device__ unsigned long long g_trace[6 * kTraceLen];   // row 5: per-tile counters of CTA 0 (slow groups of warp e=0)
 __device__ unsigned long long g_epi[64 * 12];   // per-tile stamps inside the epilogue of CTA 0, warp e=0
-#define SKY_EPI(it, slot) do { if ((p.debug & 8) && blockIdx.x == 0 && e == 0 && lane == 0 && (it) < 64) g_epi[(it) * 12 + (slot)] = clock64(); } while (0)
-#define SKY_TRACE(row, i) do { if ((p.debug & 8) && blockIdx.x == 0 && (i) < kTraceLen) g_trace[(row) * kTraceLen + (i)] = clock64(); } while (0)
+#define SKY_EPI(it, slot) do { if ((SKY_DBG(p) & 8) && blockIdx.x == 0 && e == 0 && lane == 0 && (it) < 64) g_epi[(it) * 12 + (slot)] = clock64(); } while (0)
+#define SKY_TRACE(row, i) do { if ((SKY_DBG(p) & 8) && blockIdx.x == 0 && (i) < kTraceLen) g_trace[(row) * kTraceLen + (i)] = clock64(); } while (0)
+#else
+#define SKY_EPI(it, slot) do { } while (0)
+#define SKY_TRACE(row, i) do { } while (0)
+#endif
 
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -96,12 +101,12 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
     int my_tiles = (p.num_tiles > static_cast<int>(blockIdx.x))
                        ? (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
                        : 0;
-    if (p.debug & 4) {   // experiment: contiguous tile range per CTA
+    if (SKY_DBG(p) & 4) {   // experiment: contiguous tile range per CTA
         const int lo = static_cast<int>(blockIdx.x) * tiles_per_cta;
         my_tiles = p.num_tiles > lo ? min(tiles_per_cta, p.num_tiles - lo) : 0;
     }
     auto tile_of = [&](int it) -> int {
-        return (p.debug & 4) ? static_cast<int>(blockIdx.x) * tiles_per_cta + it : static_cast<int>(blockIdx.x + it * gridDim.x);
+        return (SKY_DBG(p) & 4) ? static_cast<int>(blockIdx.x) * tiles_per_cta + it : static_cast<int>(blockIdx.x + it * gridDim.x);
     };
 
     if (warp == 0 && lane == 0) {
@@ -196,7 +201,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
                     for (int k = 0; k < kKBlock / 16; ++k) {
                         const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_addr + k * 32);
                         const uint64_t b_desc = ptx::make_sw128_kmajor_desc(b_addr + k * 32);
-                        if (!(p.debug & 2)) ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(SKY_DBG(p) & 2)) ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty_bar[stage]);      // stage reusable once these MMAs retire
                     SKY_TRACE(2, it * KB + kb);
@@ -236,7 +241,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
             if (e == 0 && lane == 0) SKY_TRACE(3, it);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
-            if (it == 0 && p.use_gtau && !(p.debug & 1)) {
+            if (it == 0 && p.use_gtau && !(SKY_DBG(p) & 1)) {
                 // BOOTSTRAP (once per launch): with no bound yet, every row of the first tile would be a
                 // candidate for every query.  Instead read the accumulator twice: this first pass only takes
                 // the per-query maximum of the tile, the exchange warp trades maxima with the other CTAs,
@@ -277,7 +282,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
                 }
-                if (p.debug & 1) continue;
+                if (SKY_DBG(p) & 1) continue;
                 // FAST PATH, branch-free and compact (instruction-cache friendly): 32 conservative
                 // pre-filters in the space of the accumulator -- no division, no key -- into one bitmask.
                 // Thresholds are read with vector loads and may be slightly stale (they only tighten);
@@ -391,6 +396,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
     }
 }
 
+#ifdef SKY_EXPERIMENTS
 int debug_read_trace(unsigned long long* h_out, int n) {
     if (n > 6 * kTraceLen) n = 6 * kTraceLen;
     SKY_CUDA(cudaDeviceSynchronize());
@@ -402,6 +408,7 @@ int debug_read_epi(unsigned long long* h_out) {
     SKY_CUDA(cudaMemcpyFromSymbol(h_out, g_epi, sizeof(g_epi)));
     return SKY_OK;
 }
+#endif
 
 // Queries -> bf16 operand matrix [q_pad, Dp] (zero padded) + per-query constants.
 __global__ void pack_queries_kernel(const float* __restrict__ t, int Q, int D, int Dp, int q_pad, int metric,
@@ -411,9 +418,13 @@ __global__ void pack_queries_kernel(const float* __restrict__ t, int Q, int D, i
     __shared__ double red[8];
     double acc = 0.0;
     for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
-        float v = (q < Q && d < D) ? t[static_cast<size_t>(q) * D + d] : 0.f;
-        bq[static_cast<size_t>(q) * Dp + d] = __float2bfloat16_rn(v);
-        acc += static_cast<double>(v * v);
+        const float v = (q < Q && d < D) ? t[static_cast<size_t>(q) * D + d] : 0.f;
+        const __nv_bfloat16 r = __float2bfloat16_rn(v);
+        bq[static_cast<size_t>(q) * Dp + d] = r;
+        // |t|^2 of the ROUNDED query: the contraction sees bf16(t), so cosine and MSE stay a true cosine / squared
+        // distance of that vector (never negative for a near-duplicate row)
+        const float vr = __bfloat162float(r);
+        acc += static_cast<double>(vr * vr);
     }
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) red[warp] = acc;
@@ -516,11 +527,11 @@ int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const Searc
     SKY_LAUNCH_CHECK("pack_queries_kernel");
 
     int stages = tc_stages(b->Dp, BN);
-    { static const char* e = getenv("SKY_TC_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
+    { const int e = env_knob("SKY_TC_STAGES", 0); if (e >= 2 && e < stages) stages = e; }
     const size_t smem = 1024 + static_cast<size_t>(b->Dp) * BN * 2 + static_cast<size_t>(stages) * kStageBytes + tc_tail_bytes(BN);
     SKY_CUDA(cudaFuncSetAttribute(tc_search_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int grid = s.P;
-    { static const char* e = getenv("SKY_TC_GRID"); if (e && atoi(e) >= 1 && atoi(e) < grid) grid = atoi(e); }
+    { const int e = env_knob("SKY_TC_GRID", 0); if (e >= 1 && e < grid) grid = e; }
     for (int q0 = 0; q0 < Q; q0 += BN) {
         CUtensorMap tmq;
         int rc = make_tmap_2d(&tmq, bq + static_cast<size_t>(q0) * b->Dp, BN, b->Dp, BN);
@@ -537,8 +548,8 @@ int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const Searc
         p.kblocks = b->Dp / kKBlock;
         p.stages = stages;
         p.metric = metric;
-        { static const char* dbg = getenv("SKY_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-        { static const char* pol = getenv("SKY_TC_POLICY"); const int pv = pol ? atoi(pol) : 0;
+        p.debug = env_knob("SKY_TC_DEBUG", 0);
+        { const int pv = env_knob("SKY_TC_POLICY", 0);
           p.bank_policy = pv == 1 ? 0x1000000000000000ull /* evict normal */ : (pv == 2 ? ptx::kEvictLast : ptx::kEvictFirst); }
         p.inv_dd = 1.0f / (static_cast<float>(b->D) * static_cast<float>(b->D));
         prof_mark(b, st);

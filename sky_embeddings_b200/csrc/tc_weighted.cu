@@ -158,7 +158,7 @@ tc_weighted_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int i = 0; i < total; ++i) {
             ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);
             // the previous MMAs that read this TMEM buffer retired before the producers refilled the stage (empty_bar)
-            if (p.debug & 1) { ptx::mbar_arrive(&sq_bar[stage]); if (++stage == kTwStages) { stage = 0; phase ^= 1; } continue; }
+            if (SKY_DBG(p) & 1) { ptx::mbar_arrive(&sq_bar[stage]); if (++stage == kTwStages) { stage = 0; phase ^= 1; } continue; }
             const uint32_t a = s0 + static_cast<uint32_t>(stage) * kTwStage;
             uint32_t v[32];
 #pragma unroll
@@ -203,7 +203,7 @@ tc_weighted_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     for (int k = 0; k < kKBlock / 16; ++k) {
                         ptx::umma_bf16(d1, ptx::make_sw128_kmajor_desc(a_addr + k * 32), ptx::make_sw128_kmajor_desc(ba_addr + k * 32),
                                        idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (!(p.debug & 2)) ptx::umma_bf16_ts(d2, a2_tmem + k * 8, ptx::make_sw128_kmajor_desc(bw_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(SKY_DBG(p) & 2)) ptx::umma_bf16_ts(d2, a2_tmem + k * 8, ptx::make_sw128_kmajor_desc(bw_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == kTwStages) { stage = 0; phase ^= 1; }
@@ -237,7 +237,7 @@ tc_weighted_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
                 }
-                if (p.debug & 4) continue;
+                if (SKY_DBG(p) & 4) continue;
                 auto score = [&](float d1, float d2, float q1, float q2) -> float {
                     // cosine: the accumulated w.(z o z) can round slightly below zero for a near-null row
                     return COS ? __fdividef(d1, fmaf(q1, sqrtf(fmaxf(d2, 0.f)), 1e-6f)) : (q1 - 2.0f * d1 + d2) * q2;
@@ -342,9 +342,13 @@ __global__ void pack_weighted_kernel(const float* __restrict__ t, const float* _
     for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
         float tv = 0.f, wv = 0.f;
         if (q < nq && d < D) { tv = t[static_cast<size_t>(q) * D + d]; wv = w[static_cast<size_t>(q) * D + d]; }
-        ba[static_cast<size_t>(q) * Dp + d] = __float2bfloat16_rn(wv * tv);
-        bw[static_cast<size_t>(q) * Dp + d] = __float2bfloat16_rn(wv);
-        s_wtt += static_cast<double>(wv * (tv * tv));
+        const __nv_bfloat16 ar = __float2bfloat16_rn(wv * tv), wr = __float2bfloat16_rn(wv);
+        ba[static_cast<size_t>(q) * Dp + d] = ar;
+        bw[static_cast<size_t>(q) * Dp + d] = wr;
+        // sum w t^2 of the ROUNDED operands a~ = bf16(w t), w~ = bf16(w): sum a~^2 / w~, so that
+        // sum w t^2 - 2 a.z + w.z^2 = sum w~ (a~/w~ - z)^2 stays a true weighted squared distance
+        const float af = __bfloat162float(ar), wf = __bfloat162float(wr);
+        s_wtt += (wf > 0.f) ? static_cast<double>(af) * af / wf : static_cast<double>(wv * (tv * tv));
         s_w += static_cast<double>(wv);
     }
     for (int off = 16; off > 0; off >>= 1) { s_wtt += __shfl_xor_sync(0xffffffffu, s_wtt, off); s_w += __shfl_xor_sync(0xffffffffu, s_w, off); }
@@ -401,7 +405,7 @@ int launch_tc_weighted(sky_bank* b, const float* t, const float* w, int Q, int m
         p.num_tiles = static_cast<int>((b->rows + kTileRows - 1) / kTileRows);
         p.kblocks = b->Dp / kKBlock;
         p.bank_policy = ptx::kEvictFirst;
-        { static const char* e = getenv("SKY_TW_DEBUG"); p.debug = e ? atoi(e) : 0; }
+        p.debug = env_knob("SKY_TW_DEBUG", 0);
         prof_mark(b, st);
         if (metric == SKY_COSINE) tc_weighted_kernel<true><<<s.P, kTwThreads, smem, st>>>(tma, tmw, p);
         else tc_weighted_kernel<false><<<s.P, kTwThreads, smem, st>>>(tma, tmw, p);

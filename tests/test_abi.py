@@ -51,6 +51,5 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
-                assert "/root/reference" not in src.replace("/root/reference/utils", "").replace(
-                    "/root/reference/similarity_search.py", "").replace("/root/reference/sky_sim_search.py", "") \
-                    or True
+                # docstrings may CITE reference files; nothing may open / import them at run time
+                assert not re.search(r"(open|load|import_module|spec_from_file_location|sys\.path\.\w+)\([^)]*/root/reference", src), f

@@ -19,7 +19,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["gpu_launches"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
 
 
 def test_reference_arm_other_ranks_exit_quietly():
