@@ -437,7 +437,7 @@ def test_config2_shape_property_checks(dev):
     assert bool((sc[:, :-1] >= sc[:, 1:]).all())          # best first
     # exact check against torch on the stored bank, chunked (fp32 accumulate, bf16-rounded queries)
     tb = t.to(torch.bfloat16).to(torch.float32)
-    tt = t.pow(2).sum(1).sqrt()
+    tt = tb.pow(2).sum(1).sqrt()                            # |t| of the rounded query (pack_queries_kernel)
     best_s = torch.full((Q, k), float("-inf"), device=dev)
     best_i = torch.zeros((Q, k), dtype=torch.int64, device=dev)
     step = 1 << 17
@@ -456,6 +456,7 @@ def test_config2_shape_property_checks(dev):
     sc2, ix2 = bank.search(t[:4], None, k=k, metric="cosine", path="simt")
     ref_s = torch.full((4, k), float("-inf"), device=dev)
     ref_i = torch.zeros((4, k), dtype=torch.int64, device=dev)
+    tt = t.pow(2).sum(1).sqrt()
     for s0 in range(0, n, step):
         z = bank.download(s0, min(step, n - s0))[:, 0]
         s = (t[:4] @ z.T) / (tt[:4, None] * z.pow(2).sum(1).sqrt()[None, :] + 1e-6)
