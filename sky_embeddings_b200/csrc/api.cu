@@ -373,14 +373,12 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
     // differently depending on the batch size
     if (tw_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q > kAutoStreamMaxQ))) {
         SearchState sw{};
-        const int grid = tc_grid(b);
+        const int grid = tc_weighted_grid(b);
         int rcw = plan_state(b, grid, Q, k, grid, &sw);
         if (rcw) return rcw;
         rcw = ensure_ws2(b, tc_weighted_scratch_bytes(b));
         if (rcw) return rcw;
-        rcw = launch_init_state(sw, grid, st);
-        if (rcw) return rcw;
-        rcw = launch_tc_weighted(b, t, w, Q, metric, sw, st);
+        rcw = launch_tc_weighted(b, t, w, Q, metric, sw, st);      // its packing kernel zeroes the exchange state
         if (rcw) return rcw;
         return launch_merge_lists(sw, metric, idx_offset, out_scores, out_idx, st);
     }
@@ -413,9 +411,7 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
         if (rc) return rc;
         rc = ensure_ws2(b, tc_scratch_bytes(b, Q));
         if (rc) return rc;
-        rc = launch_init_state(s, grid, st);
-        if (rc) return rc;
-        rc = launch_tc_search(b, t, Q, metric, s, st);
+        rc = launch_tc_search(b, t, Q, metric, s, st);              // its packing kernel zeroes the exchange state
         if (rc) return rc;
     } else {
         SimtArgs a;

@@ -49,6 +49,19 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
 
     if (tid == 0) { npool = 0; tau_s = 0u; }
     __syncthreads();
+    // list fills: issued before the bound reduction so both L2 round trips overlap
+    constexpr int kCountCache = 2048;
+    const int per = (P + kMergeThreads - 1) / kMergeThreads;
+    int mine[kCountCache / kMergeThreads];
+    int tot = 0;
+    if (P <= kCountCache) {
+#pragma unroll
+        for (int u = 0; u < kCountCache / kMergeThreads; ++u) {
+            const int pi = tid * per + u;
+            mine[u] = (u < per && pi < P) ? min(counts[static_cast<size_t>(pi) * Qtot + q], cap) : 0;
+            tot += mine[u];
+        }
+    }
     // final grid-wide bound: the k-th largest of the per-CTA best keys (see topk.cuh)
     if (use_gtau && warp == 0) {
         const uint32_t lo = exchange_reduce(gtop + q, p_stride, Qtot, k);
@@ -58,19 +71,67 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     // every composite with key >= tau must be kept; tau == 0 / disabled keeps everything valid
     const uint64_t keep_ge = (use_gtau && tau_s != 0u) ? (static_cast<uint64_t>(tau_s) << 32) : 1ull;
 
-    // all list fills first (one L2 round trip instead of one per list), then the filtered gather
-    constexpr int kCountCache = 2048;
-    __shared__ int s_n[kCountCache];
-    for (int p = tid; p < P && p < kCountCache; p += kMergeThreads) s_n[p] = counts[static_cast<size_t>(p) * Qtot + q];
-    __syncthreads();
-    for (int p = warp; p < P; p += nwarps) {
-        const int n = p < kCountCache ? s_n[p] : counts[static_cast<size_t>(p) * Qtot + q];
-        const uint64_t* e = lists + (static_cast<size_t>(p) * Qtot + q) * cap;
-        for (int i = lane; i < n; i += 32) {
-            const uint64_t v = e[i];
-            if (v >= keep_ge) {
-                const uint32_t pos = atomicAdd(&npool, 1u);
-                if (pos < kPool) pool[pos] = v;
+    // all list fills first (one L2 round trip), then ONE flat pass over the concatenation of the lists: entry j of
+    // the concatenation belongs to the list whose offset range holds j (binary search in shared memory), so every
+    // thread's loads are independent of each other -- a list-per-warp loop would pay one dependent L2 round trip
+    // per list (P / 8 of them in a row)
+    __shared__ int s_off[kCountCache + 1];
+    __shared__ int s_wsum[kMergeThreads / 32];
+    if (P <= kCountCache) {
+        // exclusive scan of the fills (loaded above): thread t owns lists [t * per, (t + 1) * per)
+        int incl = tot;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int i = 0; i < warp; ++i) wbase += s_wsum[i];
+        int run = wbase + incl - tot;
+#pragma unroll
+        for (int u = 0; u < kCountCache / kMergeThreads; ++u) {
+            const int pi = tid * per + u;
+            if (u < per && pi < P) s_off[pi] = run;
+            run += mine[u];
+        }
+        if (tid == kMergeThreads - 1) s_off[P] = run;
+        __syncthreads();
+        const int total = s_off[P];
+        for (int j0 = tid; j0 < total; j0 += 4 * kMergeThreads) {
+            uint64_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {           // four independent loads in flight per thread
+                const int j = j0 + u * kMergeThreads;
+                v[u] = 0ull;
+                if (j < total) {
+                    int lo = 0, hi = P;             // largest lo with s_off[lo] <= j
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_off[mid] <= j) lo = mid; else hi = mid;
+                    }
+                    v[u] = __ldcg(reinterpret_cast<const unsigned long long*>(lists + (static_cast<size_t>(lo) * Qtot + q) * cap + (j - s_off[lo])));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (v[u] >= keep_ge) {
+                    const uint32_t pos = atomicAdd(&npool, 1u);
+                    if (pos < kPool) pool[pos] = v[u];
+                }
+            }
+        }
+    } else {
+        for (int p = warp; p < P; p += nwarps) {
+            const int n = counts[static_cast<size_t>(p) * Qtot + q];
+            const uint64_t* e = lists + (static_cast<size_t>(p) * Qtot + q) * cap;
+            for (int i = lane; i < n; i += 32) {
+                const uint64_t v = e[i];
+                if (v >= keep_ge) {
+                    const uint32_t pos = atomicAdd(&npool, 1u);
+                    if (pos < kPool) pool[pos] = v;
+                }
             }
         }
     }

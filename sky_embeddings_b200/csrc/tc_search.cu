@@ -412,7 +412,8 @@ int debug_read_epi(unsigned long long* h_out) {
 
 // Queries -> bf16 operand matrix [q_pad, Dp] (zero padded) + per-query constants.
 __global__ void pack_queries_kernel(const float* __restrict__ t, int Q, int D, int Dp, int q_pad, int metric,
-                                    __nv_bfloat16* __restrict__ bq, float* __restrict__ qconst) {
+                                    __nv_bfloat16* __restrict__ bq, float* __restrict__ qconst, const StateInit si) {
+    state_init_gridwide(si);
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     __shared__ double red[8];
@@ -473,7 +474,7 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_
 }
 
 int launch_pack_queries(const float* t, int Q, int D, int Dp, int q_pad, int metric, void* bq, float* qconst, cudaStream_t st) {
-    pack_queries_kernel<<<q_pad, 256, 0, st>>>(t, Q, D, Dp, q_pad, metric, reinterpret_cast<__nv_bfloat16*>(bq), qconst);
+    pack_queries_kernel<<<q_pad, 256, 0, st>>>(t, Q, D, Dp, q_pad, metric, reinterpret_cast<__nv_bfloat16*>(bq), qconst, StateInit{});
     SKY_LAUNCH_CHECK("pack_queries_kernel");
     return SKY_OK;
 }
@@ -523,7 +524,9 @@ int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const Searc
     __nv_bfloat16* bq = reinterpret_cast<__nv_bfloat16*>(b->ws2);
     float* qconst = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(b->ws2) +
                                              round_up(static_cast<int64_t>(q_pad) * b->Dp * 2, 256));
-    pack_queries_kernel<<<q_pad, 256, 0, st>>>(t, Q, b->D, b->Dp, q_pad, metric, bq, qconst);
+    // the packing grid also zeroes the exchange state of this search (no separate init_state launch)
+    const StateInit si{s.gtop, s.gtau, s.counts, s.Qtot, s.p_stride, s.P};
+    pack_queries_kernel<<<q_pad, 256, 0, st>>>(t, Q, b->D, b->Dp, q_pad, metric, bq, qconst, si);
     SKY_LAUNCH_CHECK("pack_queries_kernel");
 
     int stages = tc_stages(b->Dp, BN);

@@ -11,6 +11,7 @@
 // 6 stages deep).  HBM traffic is one pass over the bank for up to 64 weighted queries -- HBM bound like K2.  Candidate sink, grid-wide bound exchange and merge are shared with K1/K2.
 #include <cuda_bf16.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "bank.cuh"
@@ -48,6 +49,81 @@ struct TwParams {
 
 __device__ __forceinline__ void tw_cp_async_16(uint32_t smem_dst, const void* gsrc, uint64_t policy) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "l"(policy) : "memory");
+}
+
+// Epilogue of one 128-row tile for one warp (thread = bank row = TMEM lane): D1 | D2 accumulators of 64 queries at
+// `taddr` -> conservative pre-filter bitmask -> exact score and insert of the survivors.  `release` runs once the
+// last accumulator chunk is in registers (the accumulator stage may then be overwritten by the next tile's MMAs).
+template <bool COS, typename Release>
+__device__ __forceinline__ void tw_score_tile(uint32_t taddr, uint32_t row, bool valid, int nq, int debug, const Sink& sink,
+                                              const float* sQ1, const float* sQ2, Release release) {
+    constexpr bool largest = COS;
+#pragma unroll 1
+    for (int c = 0; c < kTwBN / 32; ++c) {
+        uint32_t v1[32], v2[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c * 32, v1);
+        ptx::tmem_ld_32x32b_x32(taddr + kTwBN + c * 32, v2);
+        ptx::tmem_ld_wait();
+        if (c == kTwBN / 32 - 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            release();
+        }
+        if (debug & 4) continue;
+        auto score = [&](float d1, float d2, float q1, float q2) -> float {
+            // cosine: the accumulated w.(z o z) can round slightly below zero for a near-null row
+            return COS ? __fdividef(d1, fmaf(q1, sqrtf(fmaxf(d2, 0.f)), 1e-6f)) : (q1 - 2.0f * d1 + d2) * q2;
+        };
+        // FAST PATH: conservative pre-filter without square root or division.  Thresholds are read with vector
+        // loads and may be stale (they only tighten); NaN goes on to the exact test; padding queries never pass.
+        //   cosine: s >= th  <=>  d1 >= th (q1 sqrt(d2) + 1e-6); with f(x) = x |x| (monotone) this is implied by
+        //           f(d1 + 1e-6) >= f(th q1) d2, lowered by a few 1e-6 relative
+        //   MSE:    s <= th  <=>  (q1 - 2 d1 + d2) q2 <= th
+        uint32_t mbits = 0;
+        const uint32_t thf_addr = sink.thr_f + c * 32 * 4;
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+            float th[4];
+            asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(th[0]), "=f"(th[1]), "=f"(th[2]), "=f"(th[3]) : "r"(thf_addr + g4 * 16) : "memory");
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = g4 * 4 + u, q = c * 32 + j;
+                const float d1 = __uint_as_float(v1[j]), d2 = __uint_as_float(v2[j]);
+                bool pass;
+                if (COS) {
+                    const float x = d1 + 1e-6f, t2 = th[u] * sQ1[q];
+                    float rhs = t2 * fabsf(t2) * fmaxf(d2, 0.f);
+                    rhs = fmaf(-fabsf(rhs), 8e-6f, rhs);
+                    pass = !(x * fabsf(x) < rhs);
+                } else {
+                    pass = !((sQ1[q] - 2.0f * d1 + d2) * sQ2[q] > th[u]);
+                }
+                mbits |= (pass ? 1u : 0u) << j;
+            }
+        }
+        mbits = valid ? mbits : 0u;
+#pragma unroll 1
+        while (mbits) {
+            const int j = __ffs(mbits) - 1;
+            mbits &= mbits - 1;
+            const int q = c * 32 + j;
+            if (q >= nq) continue;
+            uint32_t a16[16], a8[8], a4[4], a2[2], b16[16], b8[8], b4[4], b2[2];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { a16[i] = (j & 1) ? v1[2 * i + 1] : v1[2 * i]; b16[i] = (j & 1) ? v2[2 * i + 1] : v2[2 * i]; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a8[i] = (j & 2) ? a16[2 * i + 1] : a16[2 * i]; b8[i] = (j & 2) ? b16[2 * i + 1] : b16[2 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a4[i] = (j & 4) ? a8[2 * i + 1] : a8[2 * i]; b4[i] = (j & 4) ? b8[2 * i + 1] : b8[2 * i]; }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { a2[i] = (j & 8) ? a4[2 * i + 1] : a4[2 * i]; b2[i] = (j & 8) ? b4[2 * i + 1] : b4[2 * i]; }
+            const float d1 = __uint_as_float((j & 16) ? a2[1] : a2[0]);
+            const float d2 = __uint_as_float((j & 16) ? b2[1] : b2[0]);
+            const float sv = score(d1, d2, sQ1[q], sQ2[q]);
+            sink_insert_one(sink, q, make_composite(score_to_key(sv, largest), row));
+        }
+    }
 }
 
 template <bool COS>
@@ -226,72 +302,8 @@ tc_weighted_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             __syncwarp();
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 2 * kTwBN);
-#pragma unroll 1
-            for (int c = 0; c < kTwBN / 32; ++c) {
-                uint32_t v1[32], v2[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c * 32, v1);
-                ptx::tmem_ld_32x32b_x32(taddr + kTwBN + c * 32, v2);
-                ptx::tmem_ld_wait();
-                if (c == kTwBN / 32 - 1) {
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-                }
-                if (SKY_DBG(p) & 4) continue;
-                auto score = [&](float d1, float d2, float q1, float q2) -> float {
-                    // cosine: the accumulated w.(z o z) can round slightly below zero for a near-null row
-                    return COS ? __fdividef(d1, fmaf(q1, sqrtf(fmaxf(d2, 0.f)), 1e-6f)) : (q1 - 2.0f * d1 + d2) * q2;
-                };
-                // FAST PATH: conservative pre-filter without square root or division.  Thresholds are read with vector
-                // loads and may be stale (they only tighten); NaN goes on to the exact test; padding queries never pass.
-                //   cosine: s >= th  <=>  d1 >= th (q1 sqrt(d2) + 1e-6); with f(x) = x |x| (monotone) this is implied by
-                //           f(d1 + 1e-6) >= f(th q1) d2, lowered by a few 1e-6 relative
-                //   MSE:    s <= th  <=>  (q1 - 2 d1 + d2) q2 <= th
-                uint32_t mbits = 0;
-                const uint32_t thf_addr = sink.thr_f + c * 32 * 4;
-#pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4) {
-                    float th[4];
-                    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(th[0]), "=f"(th[1]), "=f"(th[2]), "=f"(th[3]) : "r"(thf_addr + g4 * 16) : "memory");
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = g4 * 4 + u, q = c * 32 + j;
-                        const float d1 = __uint_as_float(v1[j]), d2 = __uint_as_float(v2[j]);
-                        bool pass;
-                        if (COS) {
-                            const float x = d1 + 1e-6f, t2 = th[u] * sQ1[q];
-                            float rhs = t2 * fabsf(t2) * fmaxf(d2, 0.f);
-                            rhs = fmaf(-fabsf(rhs), 8e-6f, rhs);
-                            pass = !(x * fabsf(x) < rhs);
-                        } else {
-                            pass = !((sQ1[q] - 2.0f * d1 + d2) * sQ2[q] > th[u]);
-                        }
-                        mbits |= (pass ? 1u : 0u) << j;
-                    }
-                }
-                mbits = valid ? mbits : 0u;
-#pragma unroll 1
-                while (mbits) {
-                    const int j = __ffs(mbits) - 1;
-                    mbits &= mbits - 1;
-                    const int q = c * 32 + j;
-                    if (q >= p.nq) continue;
-                    uint32_t a16[16], a8[8], a4[4], a2[2], b16[16], b8[8], b4[4], b2[2];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { a16[i] = (j & 1) ? v1[2 * i + 1] : v1[2 * i]; b16[i] = (j & 1) ? v2[2 * i + 1] : v2[2 * i]; }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { a8[i] = (j & 2) ? a16[2 * i + 1] : a16[2 * i]; b8[i] = (j & 2) ? b16[2 * i + 1] : b16[2 * i]; }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { a4[i] = (j & 4) ? a8[2 * i + 1] : a8[2 * i]; b4[i] = (j & 4) ? b8[2 * i + 1] : b8[2 * i]; }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) { a2[i] = (j & 8) ? a4[2 * i + 1] : a4[2 * i]; b2[i] = (j & 8) ? b4[2 * i + 1] : b4[2 * i]; }
-                    const float d1 = __uint_as_float((j & 16) ? a2[1] : a2[0]);
-                    const float d2 = __uint_as_float((j & 16) ? b2[1] : b2[0]);
-                    const float sv = score(d1, d2, sQ1[q], sQ2[q]);
-                    sink_insert_one(sink, q, make_composite(score_to_key(sv, largest), static_cast<uint32_t>(row)));
-                }
-            }
+            tw_score_tile<COS>(taddr, static_cast<uint32_t>(row), valid, p.nq, SKY_DBG(p), sink, sQ1, sQ2,
+                               [&]() { if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]); });
             ptx::named_bar_sync(1, 128);
             sink_prune_if_full(sink, p.nq, e, 4, hist);
             ptx::named_bar_sync(1, 128);
@@ -331,10 +343,273 @@ tc_weighted_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2w2: the same search on a CTA PAIR (cta_group::2) with the query operands RESIDENT in shared memory.
+//
+// K2w above re-streams the 2 x 8 KB query k-blocks from L2 with every 16 KB bank stage (they do not fit beside a
+// ring: 64 queries x Dp x 2 matrices = 192 KB at Dp = 768), which doubles the shared-memory fill traffic and halves
+// the ring.  One tcgen05.mma.cta_group::2 of M = 256 takes 128 bank rows from EACH CTA of the pair but only HALF of
+// the B rows from each: every CTA keeps just 32 of the 64 queries (both matrices: 96 KB at Dp = 768) resident for
+// the whole kernel and the ring carries nothing but bank tiles, landed by TMA (7 x 16 KB at Dp = 768).
+//   warp 0      bank stream (one thread): TMA of the CTA's own tiles, contiguous 16 KB (tile, k-block) boxes
+//   warp 1      MMA issuer (one thread of the EVEN CTA issues for the pair); owns the pair's TMEM allocation
+//   warp 2      grid-wide bound exchange (per CTA, as K2)
+//   warps 4-7   squarers (per CTA): z -> z o z into the CTA's own TMEM; one arrival per warp on the even CTA's barrier
+//   warps 8-11  epilogue (per CTA): own 128 rows x 64 queries, own candidate lists
+// Both CTAs walk the same number of tiles in lock-step (tile = blockIdx.x + it * gridDim.x); the odd CTA's last tile
+// may lie past the end of the bank, it then re-reads the last real tile and its rows are masked as invalid.
+// ---------------------------------------------------------------------------------------------
+constexpr int kT2Threads = 12 * 32;
+constexpr int kT2ProdWarp = 0, kT2MmaWarp = 1, kT2XchgWarp = 2, kT2SquareWarp0 = 4, kT2EpiWarp0 = 8;
+constexpr int kT2HalfN = kTwBN / 2;              // query rows resident per CTA
+constexpr int kT2BBlock = kT2HalfN * 128;        // 4 KB: one k-block of one operand half
+constexpr int kT2MaxStages = 8;                  // TMEM: 256 accumulator columns + 32 per stage <= 512
+
+struct Tw2Params {
+    TwParams w;
+    int stages;
+    int spin;       // barriers signalled from the OTHER SM are polled (no suspend hint, no back-off)
+};
+
+__device__ __forceinline__ void t2_wait_remote(uint64_t* bar, uint32_t parity, int spin) {
+    if (spin) ptx::mbar_wait(bar, parity);
+    else ptx::mbar_wait_relaxed(bar, parity, 32);
+}
+
+template <bool COS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1)
+tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_w, const Tw2Params pp) {
+    const TwParams& p = pp.w;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int KB = p.kblocks, S = pp.stages;
+    unsigned char* sBa = base;                                                      // [KB][32 rows][128 B]
+    unsigned char* sBw = sBa + static_cast<size_t>(KB) * kT2BBlock;
+    unsigned char* sA = sBw + static_cast<size_t>(KB) * kT2BBlock;                  // [S][128 rows][128 B]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + static_cast<size_t>(S) * kTwStageA);   // TMA -> squarers (per CTA)
+    uint64_t* sq_bar = full_bar + kT2MaxStages;                                     // squarers of BOTH CTAs -> MMA (even CTA)
+    uint64_t* empty_bar = sq_bar + kT2MaxStages;                                    // MMA -> producer (multicast commit)
+    uint64_t* b_full = empty_bar + kT2MaxStages;                                    // [1] resident operands landed
+    uint64_t* tmem_full = b_full + 1;                                               // [2] multicast commit
+    uint64_t* tmem_empty = tmem_full + 2;                                           // [2] epilogue warps of BOTH CTAs -> MMA
+    unsigned long long* sThr = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(tmem_empty + 2) + 15) & ~uintptr_t(15));
+    float* sQ1 = reinterpret_cast<float*>(sThr + kTwBN);
+    float* sQ2 = sQ1 + kTwBN;
+    float* sThrF = sQ2 + kTwBN;
+    int* sCnt = reinterpret_cast<int*>(sThrF + kTwBN);
+    uint32_t* sLmax = reinterpret_cast<uint32_t*>(sCnt + kTwBN);
+    uint32_t* sHist = sLmax + kTwBN;                                                // [4][256]
+    uint32_t* sTmemBase = sHist + 4 * 256;
+    volatile int* sTilesDone = reinterpret_cast<volatile int*>(sTmemBase + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool largest = COS;
+    const uint32_t rank = ptx::cluster_ctarank();           // 0 = even CTA: issues the pair's MMAs
+    const int lead = static_cast<int>(blockIdx.x) - static_cast<int>(rank);
+    // lock-step: both CTAs run as many tiles as the even CTA has
+    const int my_tiles = (p.num_tiles > lead) ? (p.num_tiles - lead + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+    auto tile_of = [&](int it) -> int { return static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x); };
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&tmap_bank);
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_w);
+        for (int s = 0; s < S; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&sq_bar[s], 8);          // 4 squarer warps x 2 CTAs
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_init(b_full, 1);
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 8); }
+        ptx::fence_barrier_init();
+        *sTilesDone = 0;
+    }
+    if (warp == kT2MmaWarp) {
+        ptx::tmem_alloc2(sTmemBase, 512);           // 2 x (D1 | D2) accumulators + S squared k-blocks, in both CTAs
+        ptx::tmem_relinquish2();
+    }
+    for (int q = tid; q < kTwBN; q += kT2Threads) {
+        sThr[q] = (q < p.nq) ? 0ull : ~0ull;
+        sThrF[q] = (q < p.nq) ? __uint_as_float(0x7FC00000u) : (largest ? INFINITY : -INFINITY);
+        sQ1[q] = p.qc1[q];
+        sQ2[q] = p.qc2[q];
+        sCnt[q] = 0;
+        sLmax[q] = 0;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();                        // the peer's barriers are initialised before anyone signals them
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *sTmemBase;
+
+    Sink sink;
+    sink.lists = p.lists + (static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0) * p.cap;
+    sink.thr = smem_addr(sThr); sink.thr_f = smem_addr(sThrF); sink.cnt = smem_addr(sCnt); sink.lmax = smem_addr(sLmax);
+    sink.cap = p.cap; sink.k = p.k; sink.largest = largest;
+
+    if (warp == kT2ProdWarp) {
+        // ===================== producer: resident query halves once, then the bank stream, all by TMA =====================
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(KB) * 2 * kT2BBlock);
+            for (int kb = 0; kb < KB; ++kb) {
+                ptx::tma_load_2d(&tmap_a, sBa + static_cast<size_t>(kb) * kT2BBlock, b_full, kb * kKBlock, static_cast<int>(rank) * kT2HalfN, ptx::kEvictLast);
+                ptx::tma_load_2d(&tmap_w, sBw + static_cast<size_t>(kb) * kT2BBlock, b_full, kb * kKBlock, static_cast<int>(rank) * kT2HalfN, ptx::kEvictLast);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int tile = min(tile_of(it), p.num_tiles - 1);
+                for (int kb = 0; kb < KB; ++kb) {
+                    t2_wait_remote(&empty_bar[stage], phase ^ 1, pp.spin);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kTwStageA);
+                    ptx::tma_load_2d(&tmap_bank, sA + static_cast<size_t>(stage) * kTwStageA, &full_bar[stage], 0,
+                                     (tile * KB + kb) * kTileRows, p.bank_policy);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= kT2SquareWarp0 && warp < kT2SquareWarp0 + 4) {
+        // ===================== squarers: (Z o Z) k-block -> this CTA's tensor memory =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t s0 = ptx::smem_u32(sA) + row * 128;
+        const uint32_t sw = static_cast<uint32_t>(row & 7);
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kTwSqBase;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int total = my_tiles * KB;
+        if (total > 0) ptx::mbar_wait_relaxed(b_full, 0, 64);    // the first sq_bar arrival also vouches for the resident operands
+        for (int i = 0; i < total; ++i) {
+            ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);
+            if (SKY_DBG(p) & 1) {      // experiment: no squaring, only the hand-off
+                __syncwarp();
+                if (lane == 0) { if (rank == 0) ptx::mbar_arrive(&sq_bar[stage]); else ptx::mbar_arrive_cluster(&sq_bar[stage], 0); }
+                if (++stage == S) { stage = 0; phase ^= 1; }
+                continue;
+            }
+            const uint32_t a = s0 + static_cast<uint32_t>(stage) * kTwStageA;
+            uint32_t v[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3]) : "r"(a + ((c ^ sw) << 4)));
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+                __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&v[u]);
+                x = __hmul2(x, x);
+                v[u] = *reinterpret_cast<uint32_t*>(&x);
+            }
+            ptx::tmem_st_32x32b_x32(t0 + stage * kTwSqCols, v);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) ptx::mbar_arrive(&sq_bar[stage]);
+                else ptx::mbar_arrive_cluster(&sq_bar[stage], 0);
+            }
+            if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == kT2MmaWarp) {
+        // ===================== MMA issuer: one thread of the even CTA drives both SMs =====================
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * kTileRows, kTwBN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                t2_wait_remote(&tmem_empty[acc], acc_phase ^ 1, pp.spin);
+                ptx::tc_fence_after();
+                const uint32_t d1 = tmem_base + static_cast<uint32_t>(acc * 2 * kTwBN);
+                const uint32_t d2 = d1 + kTwBN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    // 8 arrivals: each squarer warp of either CTA saw its own stage land (and, first time, its resident
+                    // operands) and finished writing the squared copy
+                    t2_wait_remote(&sq_bar[stage], phase, pp.spin);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(sA + static_cast<size_t>(stage) * kTwStageA);
+                    const uint32_t ba_addr = ptx::smem_u32(sBa + static_cast<size_t>(kb) * kT2BBlock);
+                    const uint32_t bw_addr = ptx::smem_u32(sBw + static_cast<size_t>(kb) * kT2BBlock);
+                    const uint32_t a2_tmem = tmem_base + kTwSqBase + stage * kTwSqCols;
+#pragma unroll
+                    for (int k = 0; k < kKBlock / 16; ++k) {
+                        ptx::umma2_bf16(d1, ptx::make_sw128_kmajor_desc(a_addr + k * 32), ptx::make_sw128_kmajor_desc(ba_addr + k * 32),
+                                        idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(SKY_DBG(p) & 2)) ptx::umma2_bf16_ts(d2, a2_tmem + k * 8, ptx::make_sw128_kmajor_desc(bw_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma2_commit_mc(&empty_bar[stage], 0b11);      // both producers may refill the stage
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma2_commit_mc(&tmem_full[acc], 0b11);            // both epilogues may read their accumulators
+            }
+        }
+    } else if (warp >= kT2EpiWarp0 && warp < kT2EpiWarp0 + 4) {
+        // ===================== epilogue (own 128 rows, all 64 queries) =====================
+        const int e = warp - kT2EpiWarp0;
+        const int quarter = warp & 3;
+        const uint32_t hist = smem_addr(sHist + e * 256);
+        for (int it = 0; it < my_tiles; ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int64_t row = static_cast<int64_t>(tile_of(it)) * kTileRows + quarter * 32 + lane;
+            const bool valid = row < p.rows;
+            if (lane == 0) { if (pp.spin) ptx::mbar_wait(&tmem_full[acc], acc_phase); else ptx::mbar_wait_relaxed(&tmem_full[acc], acc_phase, 128); }
+            __syncwarp();
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 2 * kTwBN);
+            tw_score_tile<COS>(taddr, static_cast<uint32_t>(row), valid, p.nq, SKY_DBG(p), sink, sQ1, sQ2, [&]() {
+                if (lane == 0) {
+                    if (rank == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+                    else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+                }
+            });
+            ptx::named_bar_sync(1, 128);
+            sink_prune_if_full(sink, p.nq, e, 4, hist);
+            ptx::named_bar_sync(1, 128);
+            if (e == 0 && lane == 0) *sTilesDone = it + 1;
+        }
+        ptx::named_bar_sync(1, 128);
+        for (int q = e * 32 + lane; q < p.nq; q += 128) {
+            p.counts[static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q] = static_cast<int>(lds_u32(sink.cnt + q * 4));
+            const uint32_t mine = lds_u32(sink.lmax + q * 4);
+            if (p.use_gtau && mine) st_cg_u32(p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + q, mine);
+        }
+    } else if (warp == kT2XchgWarp) {
+        // ===================== grid-wide bound exchange (as K2) =====================
+        if (p.use_gtau && my_tiles > 0) {
+            uint32_t* my_row = p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0;
+            const int rq = static_cast<int>(blockIdx.x) % p.nq;
+            int round = 0;
+            uint32_t last_pub[kTwBN / 32] = {};
+            uint32_t last_lo = 0;
+            while (*sTilesDone < my_tiles) {
+                exchange_publish_changed(sink, p.nq, my_row, last_pub);
+                const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot, p.k);
+                if (lane == 0 && lo > last_lo) atomicMax(p.gtau + p.q0 + rq, lo);
+                last_lo = lo > last_lo ? lo : last_lo;
+                for (int q = lane; q < p.nq; q += 32) exchange_apply(sink, q, ld_cg_u32(p.gtau + p.q0 + q));
+                ++round;
+                __nanosleep(round < 24 ? 200 : 3000);
+            }
+        }
+    }
+
+    // neither CTA may leave (or free tensor memory) while the pair's MMAs still read its shared / tensor memory
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();
+    if (warp == kT2MmaWarp) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc2(tmem_base, 512);
+    }
+}
+
 // a = w o t and w as bf16 operand matrices [64, Dp] (zero padded) + per-query constants
 __global__ void pack_weighted_kernel(const float* __restrict__ t, const float* __restrict__ w, int nq, int D, int Dp, int metric,
                                      __nv_bfloat16* __restrict__ ba, __nv_bfloat16* __restrict__ bw,
-                                     float* __restrict__ qc1, float* __restrict__ qc2) {
+                                     float* __restrict__ qc1, float* __restrict__ qc2, const StateInit si) {
+    state_init_gridwide(si);
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     __shared__ double red[2][8];
@@ -376,6 +651,33 @@ size_t tc_weighted_scratch_bytes(const sky_bank* b) {
     return 2 * static_cast<size_t>(kTwBN) * b->Dp * 2 + 2 * kTwBN * sizeof(float) + 512;
 }
 
+static size_t tw2_tail_bytes() {
+    return (3 * kT2MaxStages + 1 + 4) * sizeof(uint64_t) + 16 + kTwBN * (8 + 5 * 4) + 4 * 256 * 4 + 16;
+}
+
+// ring depth of the CTA-pair kernel (0 = the resident query halves do not leave room for a useful ring)
+static int tw2_stages(int Dp) {
+    const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - tw2_tail_bytes();
+    const size_t resident = static_cast<size_t>(Dp / kKBlock) * 2 * kT2BBlock;
+    if (resident + 4 * kTwStageA > budget) return 0;
+    size_t s = (budget - resident) / kTwStageA;
+    if (s > kT2MaxStages) s = kT2MaxStages;
+    return static_cast<int>(s);
+}
+
+static bool tw2_usable(const sky_bank* b) {
+    return b->tmap_ready && b->num_sms >= 2 && tw2_stages(b->Dp) >= 4 && env_knob("SKY_TW_PAIR", 1) != 0;
+}
+
+// CTAs of the weighted tensor scorer: the pair kernel needs an even grid
+int tc_weighted_grid(const sky_bank* b) {
+    if (!tw2_usable(b)) return tc_grid(b);
+    const int64_t tiles = (b->rows + kTileRows - 1) / kTileRows;
+    const int64_t want = (tiles + 1) & ~static_cast<int64_t>(1);
+    const int cap = b->num_sms & ~1;
+    return static_cast<int>(want < cap ? want : cap);
+}
+
 // scratch (bank->ws2): Ba [64, Dp] bf16 | Bw [64, Dp] bf16 | qc1 [64] | qc2 [64]; one launch per 64 queries
 int launch_tc_weighted(sky_bank* b, const float* t, const float* w, int Q, int metric, const SearchState& s, cudaStream_t st) {
     unsigned char* ws = reinterpret_cast<unsigned char*>(b->ws2);
@@ -383,18 +685,28 @@ int launch_tc_weighted(sky_bank* b, const float* t, const float* w, int Q, int m
     __nv_bfloat16* bw = ba + static_cast<size_t>(kTwBN) * b->Dp;
     float* qc1 = reinterpret_cast<float*>(ws + round_up(2 * static_cast<int64_t>(kTwBN) * b->Dp * 2, 256));
     float* qc2 = qc1 + kTwBN;
-    const size_t smem = 1024 + static_cast<size_t>(kTwStages) * kTwStage + (3 * kTwStages + 4) * 8 + kTwBN * (8 + 5 * 4) + 4 * 256 * 4 + 64;
-    if (metric == SKY_COSINE) SKY_CUDA(cudaFuncSetAttribute(tc_weighted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    else SKY_CUDA(cudaFuncSetAttribute(tc_weighted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const bool pair = tw2_usable(b) && (s.P % 2) == 0;
+    const int stages2 = pair ? tw2_stages(b->Dp) : 0;
+    const size_t smem = pair ? 1024 + static_cast<size_t>(b->Dp / kKBlock) * 2 * kT2BBlock + static_cast<size_t>(stages2) * kTwStageA + tw2_tail_bytes()
+                             : 1024 + static_cast<size_t>(kTwStages) * kTwStage + (3 * kTwStages + 4) * 8 + kTwBN * (8 + 5 * 4) + 4 * 256 * 4 + 64;
+    if (pair) {
+        if (metric == SKY_COSINE) SKY_CUDA(cudaFuncSetAttribute(tc_weighted2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        else SKY_CUDA(cudaFuncSetAttribute(tc_weighted2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    } else {
+        if (metric == SKY_COSINE) SKY_CUDA(cudaFuncSetAttribute(tc_weighted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        else SKY_CUDA(cudaFuncSetAttribute(tc_weighted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    }
     for (int q0 = 0; q0 < Q; q0 += kTwBN) {
         const int nq = (Q - q0 < kTwBN) ? (Q - q0) : kTwBN;
         pack_weighted_kernel<<<kTwBN, 256, 0, st>>>(t + static_cast<size_t>(q0) * b->D, w + static_cast<size_t>(q0) * b->D, nq, b->D, b->Dp,
-                                                   metric, ba, bw, qc1, qc2);
+                                                   metric, ba, bw, qc1, qc2,
+                                                   q0 == 0 ? StateInit{s.gtop, s.gtau, s.counts, s.Qtot, s.p_stride, s.P} : StateInit{});
         SKY_LAUNCH_CHECK("pack_weighted_kernel");
         CUtensorMap tma, tmw;
-        int rc = make_tmap_2d(&tma, ba, kTwBN, b->Dp, kTwBN);
+        // box = the rows one CTA keeps: all 64 (streamed per stage) or its resident half of 32 (pair kernel)
+        int rc = make_tmap_2d(&tma, ba, kTwBN, b->Dp, pair ? kT2HalfN : kTwBN);
         if (rc) return rc;
-        rc = make_tmap_2d(&tmw, bw, kTwBN, b->Dp, kTwBN);
+        rc = make_tmap_2d(&tmw, bw, kTwBN, b->Dp, pair ? kT2HalfN : kTwBN);
         if (rc) return rc;
         TwParams p;
         p.bank = reinterpret_cast<const unsigned char*>(b->data);
@@ -407,7 +719,26 @@ int launch_tc_weighted(sky_bank* b, const float* t, const float* w, int Q, int m
         p.bank_policy = ptx::kEvictFirst;
         p.debug = env_knob("SKY_TW_DEBUG", 0);
         prof_mark(b, st);
-        if (metric == SKY_COSINE) tc_weighted_kernel<true><<<s.P, kTwThreads, smem, st>>>(tma, tmw, p);
+        if (pair) {
+            Tw2Params pp;
+            pp.w = p;
+            pp.w.bank_policy = env_knob("SKY_TW2_POLICY", 0) == 1 ? ptx::kEvictFirst : 0x1000000000000000ull;   // evict-normal, as K2b's bank boxes
+            pp.stages = stages2;
+            { const int e = env_knob("SKY_TW2_STAGES", 0); if (e >= 2 && e < stages2) pp.stages = e; }
+            pp.spin = env_knob("SKY_TW2_SPIN", 1);
+            if (env_knob("SKY_TW2_OCC", 0)) {
+                int ncl = -1;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(s.P); cfg.blockDim = dim3(kT2Threads); cfg.dynamicSmemBytes = smem;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                cudaOccupancyMaxActiveClusters(&ncl, tc_weighted2_kernel<true>, &cfg);
+                fprintf(stderr, "[sky] K2w2 grid %d, smem %zu, stages %d, max active clusters %d\n", s.P, smem, pp.stages, ncl);
+            }
+            if (metric == SKY_COSINE) tc_weighted2_kernel<true><<<s.P, kT2Threads, smem, st>>>(b->tmap_bank, tma, tmw, pp);
+            else tc_weighted2_kernel<false><<<s.P, kT2Threads, smem, st>>>(b->tmap_bank, tma, tmw, pp);
+        } else if (metric == SKY_COSINE) tc_weighted_kernel<true><<<s.P, kTwThreads, smem, st>>>(tma, tmw, p);
         else tc_weighted_kernel<false><<<s.P, kTwThreads, smem, st>>>(tma, tmw, p);
         prof_mark(b, st);
         SKY_LAUNCH_CHECK("tc_weighted_kernel");

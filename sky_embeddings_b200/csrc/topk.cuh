@@ -279,6 +279,22 @@ __device__ __forceinline__ void exchange_apply(const Sink& s, int q, uint32_t lo
     if (lo != 0u) sink_raise(s, q, (static_cast<uint64_t>(lo) << 32) - 1ull);
 }
 
+// Zero the grid-wide exchange state of a search (gtop / gtau / counts) from inside another kernel's grid: the query
+// packing kernels of the tensor paths do this on the side, which saves the separate init_state launch.
+struct StateInit {
+    uint32_t* gtop; uint32_t* gtau; int* counts;
+    int Qtot, p_stride, P;
+};
+__device__ __forceinline__ void state_init_gridwide(const StateInit& si) {
+    if (!si.gtop) return;
+    const int n = si.Qtot * (si.p_stride > si.P ? si.p_stride : si.P);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i < si.Qtot * si.p_stride) si.gtop[i] = 0u;
+        if (i < si.Qtot * si.P) si.counts[i] = 0;
+        if (i < si.Qtot) si.gtau[i] = 0u;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Block-level exact top-k over a virtual array fetch(j), j in [0, n): 0 = empty entry.
 // Radix-selects the k-th largest, gathers the winners into sel[kpad] (smem, kpad = pow2 >= k),
