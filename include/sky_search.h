@@ -146,6 +146,27 @@ SKY_API int sky_search_pixels(sky_bank_t* bank, const float* q, const unsigned c
 SKY_API int sky_score_pixels(sky_bank_t* bank, const float* q, const unsigned char* qmask, int Q, int64_t item0,
                      int64_t n_items, float* out_scores, void* stream);
 
+/* ---- pixel-side preparation in front of the bank -------------------------
+ * S/N pre-filter of the h5 search driver: calculate_snr (utils/misc.py:119-163) per image and channel,
+ *   snr = mean(central n x n pixels) / (std(all other pixels, ddof 0) + 1e-8), NaN pixels propagating as in numpy;
+ * out_snr[n_items, C] (may be NULL) and out_min[n_items] = nanmin over the first n_min_channels channels (may be NULL;
+ * similarity_search.py:127 takes the first five).  The caller keeps rows with lo < out_min < hi (:130).
+ * cutouts: device pointer [n_items, C, H, W] f32, H == W.  device < 0: taken from the pointer. */
+SKY_API int sky_pixel_snr(const float* cutouts, int64_t n_items, int C, int H, int W, int n_central_pix,
+                  int n_min_channels, float* out_snr, float* out_min, int device, void* stream);
+/* same over items [item0, item0 + n_items) of a pixel bank (its cutouts are [C, H, W] with C*H*W pixels). */
+SKY_API int sky_pixel_bank_snr(const sky_bank_t* bank, int C, int H, int W, int64_t item0, int64_t n_items,
+                       int n_central_pix, int n_min_channels, float* out_snr, float* out_min, void* stream);
+/* FITS-tile streaming: cutout i = clip(tile[:, h0_i : h0_i + size, w0_i : w0_i + size]) with (h0, w0) = coords[i]
+ * (overlapping_cutouts, utils/dataloaders.py:511-536; clipping :657-661; the coordinate list of
+ * generate_overlap_coords :481-509 comes from the host).  tile [C, H, W] f32, coords [n, 2] i32, out [n, C, size, size];
+ * pixel_min / pixel_max = NaN disables that bound; NaN pixels stay NaN. */
+SKY_API int sky_tile_cutouts(const float* tile, int C, int H, int W, const int32_t* coords, int64_t n, int size,
+                     float pixel_min, float pixel_max, float* out, int device, void* stream);
+/* h5 item path (utils/dataloaders.py:291-300, :685-700): clip, and central size x size crop of [n, C, Hs, Ws]. */
+SKY_API int sky_center_clip(const float* src, int64_t n, int C, int Hs, int Ws, int size, float pixel_min,
+                    float pixel_max, float* out, int device, void* stream);
+
 /* merge R candidate lists per query into one top-k_out, best first: the shard merge after the
  * NCCL all-gather, and the running merge of update_best_scores (utils/similarity.py:18-35).
  * scores[R,Q,k_in] f32, idx[R,Q,k_in] i64 (idx < 0 = empty slot). */

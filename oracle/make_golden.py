@@ -212,6 +212,119 @@ def c1_cases(ref):
     return out
 
 
+def ingest_inputs(seed=synth.BASE_SEED):
+    """Seeded inputs of the ingest fixtures (shared with tests/golden_inputs.py): cutouts with a central source of
+    random brightness (so S/N spreads over the reference's default window [2, 7]) and a 3-band tile."""
+    n, C, S = 48, 6, 64
+    x = synth.cutouts(n, C, S, S, seed=seed, stream=41, nan_frac=0.0, nan_chan_p=0.1)     # missing bands only
+    rng = np.random.Generator(np.random.PCG64([seed, 42]))
+    yy, xx = np.mgrid[0:S, 0:S].astype(np.float32)
+    blob = np.exp(-((yy - 31.5) ** 2 + (xx - 31.5) ** 2) / (2 * 3.0 ** 2)).astype(np.float32)
+    amp = (rng.random((n, C)) * 12.0).astype(np.float32)
+    x = (x + amp[:, :, None, None] * blob).astype(np.float32)
+    x[5] = np.nan                      # a fully missing item
+    x[3, 1, 30, 30] = np.nan           # one NaN pixel in the central region / in the surround: that channel's S/N is NaN
+    x[4, 2, 2, 60] = np.nan
+    x[9, 5] = 100.0                    # sixth channel is ignored by the nanmin over the first five
+    tile = synth.cutouts(1, 3, 200, 173, seed=seed, stream=43, nan_frac=0.01, nan_chan_p=0.0)[0]
+    tile[1, 100:, :] = np.nan
+    tile = tile * 4.0                  # values below the -3 clip
+    return x, tile
+
+
+def ingest_cases(ref):
+    """S/N pre-filter (utils/misc.py:119-163 + similarity_search.py:124-130), overlap coordinates and tile cutouts
+    (utils/dataloaders.py:481-536) and extract_center (:685-700), by executing the reference's functions."""
+    from oracle.ref_harness import load_reference_module
+    misc = load_reference_module("utils/misc.py", "ref_misc")
+    dl = load_reference_module("utils/dataloaders.py", "ref_dataloaders")
+    out = {}
+    x, tile = ingest_inputs()
+    out["checksum"] = np.array(checksum(x, tile))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        snr = misc.calculate_snr(x, 8)
+        mn = np.nanmin(snr[:, :5], axis=(1))                                     # similarity_search.py:127
+    out["snr"] = snr.astype(np.float32)
+    out["min_snr"] = mn.astype(np.float32)
+    out["snr_range"] = np.array([2.0, 7.0])
+    out["test_indices"] = np.where((mn > 2.0) & (mn < 7.0))[0].astype(np.int64)  # :130
+    shapes = [(200, 173, 64, 0.4), (128, 128, 64, 0.5), (112, 112, 64, 0.25), (65, 64, 64, 0.0), (300, 90, 32, 0.6),
+              (100, 100, 64, 0.4)]
+    out["coord_cases"] = np.array(shapes, dtype=np.float64)
+    for i, (H, W, size, ov) in enumerate(shapes):
+        out[f"coords.{i}"] = np.array(dl.generate_overlap_coords((H, W), size, ov), dtype=np.int32).reshape(-1, 2)
+
+    def pix_to_radec(h, w):            # an affine stand-in for the WCS call (argument order as the reference passes them)
+        h, w = np.asarray(h, np.float64), np.asarray(w, np.float64)
+        return 30.0 + 1e-3 * h + 1e-5 * w, -5.0 + 2e-3 * w - 1e-5 * h
+    cut, ra_dec = dl.overlapping_cutouts(tile, 64, 0.4, pix_to_radec)
+    cut = cut.copy()
+    cut[cut < -3.0] = -3.0                                                       # utils/dataloaders.py:657-659
+    out["tile_ra_dec"] = ra_dec.astype(np.float32)
+    out["tile_cutouts_sha"] = np.array(hashlib.sha256(np.ascontiguousarray(cut.astype(np.float32)).tobytes()).hexdigest())
+    out["tile_cutouts_first"] = cut[:2].astype(np.float32)
+    big = synth.cutouts(3, 5, 96, 96, seed=synth.BASE_SEED, stream=44)
+    out["center64_sha"] = np.array(hashlib.sha256(np.ascontiguousarray(
+        np.stack([dl.extract_center(b, 64) for b in big]).astype(np.float32)).tobytes()).hexdigest())
+    return out
+
+
+def cli_cases(ref):
+    """similarity_search.py's pipeline (:122-181) on small inputs, every numeric step by the reference's own code:
+    calculate_snr + the S/N window (utils/misc.py, similarity_search.py:124-130), mae_latent (utils/eval_fns.py:72-140,
+    no augmentation so that it is deterministic), mae_simsearch (:169-171).  The encoder is the mim_1-shaped stub; the
+    loaders are in-memory equivalents of H5Dataset + DataLoader(shuffle=False) (clip at -3, zeros mask, [ra, dec])."""
+    from oracle.ref_harness import load_reference_module
+    from tests.golden_inputs import cli_inputs
+    from tests.stub_encoder import StubViT
+    misc = load_reference_module("utils/misc.py", "ref_misc")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(load_reference_module.__globals__["ref_path"]("utils/eval_fns.py"))))
+    ev = load_reference_module("utils/eval_fns.py", "ref_eval_fns")
+    inp = cli_inputs()
+    out = {"checksum": np.array(checksum(inp["test"]["cutouts"], inp["target"]["cutouts"]))}
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        snr = np.nanmin(misc.calculate_snr(inp["test"]["cutouts"], 8)[:, :5], axis=(1))
+    test_indices = np.where((snr > 2) & (snr < 7))[0]
+    out["test_indices"] = test_indices.astype(np.int64)
+    out["min_snr"] = snr.astype(np.float32)
+
+    class Loader:
+        def __init__(self, d, indices, bs):
+            self.d, self.idx, self.bs = d, np.asarray(indices), bs
+
+        def __len__(self):
+            return (len(self.idx) + self.bs - 1) // self.bs
+
+        def __iter__(self):
+            for s in range(0, len(self.idx), self.bs):
+                r = self.idx[s:s + self.bs]
+                x = self.d["cutouts"][r].copy()
+                x[x < -3.0] = -3.0
+                t = torch.from_numpy(x)
+                yield t, torch.zeros_like(t), torch.from_numpy(np.stack((self.d["ra"][r], self.d["dec"][r]), -1))
+
+    model = torch.nn.DataParallel(StubViT(seed=0))          # the reference reads model.module.* (eval_fns.py:118)
+    tgt_i = [1, 2, 4]
+    target_latent, target_images = quiet(ev.mae_latent, model, Loader(inp["target"], tgt_i, 64), "cpu", return_images=True,
+                                         apply_augmentations=False, num_augmentations=64, remove_cls=False)
+    out["target_indices"] = np.array(tgt_i)
+    out["target_features_sum"] = target_latent.double().sum(dim=(1, 2)).numpy()
+    out["target_images_sha"] = np.array(hashlib.sha256(target_images.numpy().tobytes()).hexdigest())
+    for mp, name in ((True, "maxpool"), (False, "patches")):
+        imgs, lat, ra, sc = quiet(ref.mae_simsearch, model, target_latent, Loader(inp["test"], test_indices, 64), "cpu",
+                                  metric="cosine", combine="min", use_weights=True, max_pool=mp, cls_token=False,
+                                  nested_batches=False, n_save=12)
+        out[f"test_scores.{name}"] = sc.numpy()
+        out[f"test_ra_decs.{name}"] = ra.numpy()
+        out[f"test_images_sum.{name}"] = imgs.double().nansum(dim=(1, 2, 3)).numpy()
+        out[f"test_features_sum.{name}"] = lat.double().sum(dim=(1, 2)).numpy()
+    return out
+
+
 def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -220,7 +333,8 @@ def main():
     only = sys.argv[1:]
     for name, fn in (("simsearch_small", simsearch_cases), ("simsearch_mim1_shape", mim1_shape_case),
                      ("short_bank", short_bank_case), ("compute_similarity", compute_similarity_cases),
-                     ("update_best", update_best_cases), ("pixel_small", pixel_cases), ("c1_mim1_stub", c1_cases)):
+                     ("update_best", update_best_cases), ("pixel_small", pixel_cases), ("c1_mim1_stub", c1_cases),
+                     ("ingest", ingest_cases), ("cli_small", cli_cases)):
         if only and name not in only:
             continue
         if name == "c1_mim1_stub":

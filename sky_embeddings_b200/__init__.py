@@ -7,7 +7,8 @@ teaghan/sky_embeddings (utils/similarity.py as driven by similarity_search.py / 
 Everything numeric runs in libskysearch.so (hand-written sm_100a CUDA behind a C ABI,
 include/sky_search.h); importing the search API without the built library raises.
 """
-__all__ = ["Bank", "PixelBank", "bank_from_loader", "resident_simsearch", "merge_candidates", "ShardedBank", "sharded_search", "shard_range"]
+__all__ = ["Bank", "PixelBank", "bank_from_loader", "resident_simsearch", "merge_candidates", "ShardedBank", "sharded_search", "shard_range",
+           "H5Cutouts", "H5CutoutLoader", "TileLoader"]
 
 
 def __getattr__(name):
@@ -20,4 +21,7 @@ def __getattr__(name):
     if name in ("bank_from_loader", "resident_simsearch"):
         from . import feeder
         return getattr(feeder, name)
+    if name in ("H5Cutouts", "H5CutoutLoader", "TileLoader"):
+        from . import ingest
+        return getattr(ingest, name)
     raise AttributeError(name)

@@ -44,6 +44,10 @@ SIGNATURES = {
     "sky_pixel_bank_upload": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "sky_search_pixels": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]),
     "sky_score_pixels": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _vp]),
+    "sky_pixel_snr": (_i, [_vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sky_pixel_bank_snr": (_i, [_vp, _i, _i, _i, _i64, _i64, _i, _i, _vp, _vp, _vp]),
+    "sky_tile_cutouts": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, C.c_float, C.c_float, _vp, _i, _vp]),
+    "sky_center_clip": (_i, [_vp, _i64, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _i, _vp]),
     "sky_merge_candidates": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sky_merge_candidates_strided": (_i, [_vp, _vp, _i, _i, _i, _i64, _i64, _i, _i, _vp, _vp, _i, _vp]),
     "sky_profile_enable": (_i, [_vp, _i]),

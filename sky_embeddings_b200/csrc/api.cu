@@ -604,6 +604,66 @@ int sky_score_pixels(sky_bank_t* b, const float* q, const unsigned char* qmask, 
     return pixel_impl(b, q, qmask, Q, 1, 0, nullptr, nullptr, item0, n_items, out_scores, static_cast<cudaStream_t>(stream));
 }
 
+static int device_of(const void* ptr, int device, const char* what) {
+    if (device >= 0) return device;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, ptr) != cudaSuccess || pa.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return set_error(SKY_ERR_ARG, "%s is not a device pointer (there is no CPU fallback)", what);
+    }
+    return pa.device;
+}
+
+int sky_pixel_snr(const float* cutouts, int64_t n_items, int C, int H, int W, int n_central_pix, int n_min_channels,
+                  float* out_snr, float* out_min, int device, void* stream) {
+    if (!cutouts || (!out_snr && !out_min)) return set_error(SKY_ERR_ARG, "NULL argument");
+    if (n_items < 0 || C < 1 || H < 1 || W != H) return set_error(SKY_ERR_ARG, "bad cutout shape [%lld, %d, %d, %d] (square images)", (long long)n_items, C, H, W);
+    if (n_central_pix < 1 || n_central_pix >= H) return set_error(SKY_ERR_ARG, "n_central_pix=%d must be in [1, %d)", n_central_pix, H);
+    if (n_items > 0x7FFFFFFFll) return set_error(SKY_ERR_UNSUPPORTED, "at most 2^31-1 cutouts per call");
+    const int dev = device_of(cutouts, device, "cutouts");
+    if (dev < 0) return dev;
+    DeviceGuard g(dev);
+    if (!g.ok) return set_error(SKY_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
+    count_launch(n_items > 0 ? 1 : 0);
+    return launch_snr(cutouts, n_items, C, H, W, n_central_pix, n_min_channels < C ? n_min_channels : C, out_snr, out_min,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int sky_pixel_bank_snr(const sky_bank_t* b, int C, int H, int W, int64_t item0, int64_t n_items, int n_central_pix,
+                       int n_min_channels, float* out_snr, float* out_min, void* stream) {
+    if (!b) return set_error(SKY_ERR_ARG, "bank is NULL");
+    if (!b->pixel) return set_error(SKY_ERR_STATE, "not a pixel bank");
+    if (static_cast<int64_t>(C) * H * W != b->D) return set_error(SKY_ERR_ARG, "C*H*W=%lld differs from the bank's %d pixels per cutout", (long long)C * H * W, b->D);
+    if (item0 < 0 || n_items < 0 || item0 + n_items > b->n_items) return set_error(SKY_ERR_ARG, "item range outside the bank");
+    return sky_pixel_snr(reinterpret_cast<const float*>(b->data) + static_cast<size_t>(item0) * b->D, n_items, C, H, W,
+                         n_central_pix, n_min_channels, out_snr, out_min, b->device, stream);
+}
+
+int sky_tile_cutouts(const float* tile, int C, int H, int W, const int32_t* coords, int64_t n, int size, float pixel_min,
+                     float pixel_max, float* out, int device, void* stream) {
+    if (!tile || (!coords && n > 0) || (!out && n > 0)) return set_error(SKY_ERR_ARG, "NULL argument");
+    if (C < 1 || size < 1 || H < size || W < size || n < 0) return set_error(SKY_ERR_ARG, "bad tile / cutout shape");
+    const int dev = device_of(tile, device, "tile");
+    if (dev < 0) return dev;
+    DeviceGuard g(dev);
+    if (!g.ok) return set_error(SKY_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
+    count_launch(n > 0 ? 1 : 0);
+    return launch_tile_cutouts(tile, C, H, W, coords, n, size, pixel_min, pixel_max, out, static_cast<cudaStream_t>(stream));
+}
+
+int sky_center_clip(const float* src, int64_t n, int C, int Hs, int Ws, int size, float pixel_min, float pixel_max,
+                    float* out, int device, void* stream) {
+    if ((!src || !out) && n > 0) return set_error(SKY_ERR_ARG, "NULL argument");
+    if (C < 1 || size < 1 || Hs < size || Ws < size || n < 0) return set_error(SKY_ERR_ARG, "bad cutout shape");
+    if (n == 0) return SKY_OK;
+    const int dev = device_of(src, device, "src");
+    if (dev < 0) return dev;
+    DeviceGuard g(dev);
+    if (!g.ok) return set_error(SKY_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
+    count_launch(1);
+    return launch_center_clip(src, n, C, Hs, Ws, size, pixel_min, pixel_max, out, static_cast<cudaStream_t>(stream));
+}
+
 int sky_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int k_out, int metric,
                          float* out_scores, int64_t* out_idx, int device, void* stream) {
     if (!scores || !idx || !out_scores || !out_idx) return set_error(SKY_ERR_ARG, "NULL argument");

@@ -98,6 +98,14 @@ int launch_pixel_fold(const float* q, const unsigned char* mask, int64_t n, floa
 int launch_pixel_search(const sky_bank* b, const float* qp, int Q, int64_t row_lo, int64_t row_hi, const SearchState& s,
                         int grid, int qc, float* emit, cudaStream_t st);
 
+// pixel_prep.cu
+int launch_snr(const float* img, int64_t n_items, int C, int H, int W, int n_central, int n_min_channels, float* out_snr,
+               float* out_min, cudaStream_t st);
+int launch_tile_cutouts(const float* tile, int C, int H, int W, const int* coords, int64_t n, int size, float lo, float hi,
+                        float* out, cudaStream_t st);
+int launch_center_clip(const float* src, int64_t n, int C, int Hs, int Ws, int size, float lo, float hi, float* out,
+                       cudaStream_t st);
+
 // tc_search.cu
 bool tc_supported(const sky_bank* b, int metric, bool weighted, int n_top);
 int tc_grid(const sky_bank* b);

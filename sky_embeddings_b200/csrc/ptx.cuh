@@ -119,6 +119,20 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// One lane of the (fully converged) warp is elected; every lane gets the same answer for the same mask.  The MMA
+// issuer runs warp-converged and only the tcgen05 instructions sit under this predicate, so their operands stay in
+// uniform registers (inside an `if (lane == 0)` region ptxas wraps every UTCHMMA in an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY loop: ~17 instructions and ~100 cycles per MMA, which bounds kernels that issue small-N MMAs).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
+
 // ---- CTA pair (cta_group::2): two SMs of one TPC run ONE tcgen05.mma of M = 256 ------------------
 // Each CTA supplies its own 128 rows of A (shared memory or TMEM, same offset in both CTAs) and its own N/2 rows of
 // B; each CTA's TMEM receives the full N columns for its 128 rows.  Only the even-rank CTA issues MMAs / commits.

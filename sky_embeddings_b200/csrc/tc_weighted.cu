@@ -511,37 +511,48 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
             if (++stage == S) { stage = 0; phase ^= 1; }
         }
     } else if (warp == kT2MmaWarp) {
-        // ===================== MMA issuer: one thread of the even CTA drives both SMs =====================
-        if (rank == 0 && lane == 0) {
+        // ===================== MMA issuer: the even CTA's warp drives both SMs =====================
+        // The warp stays converged (lane 0 polls, everyone computes the descriptors); one elected lane issues.
+        if (rank == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * kTileRows, kTwBN);
+            const uint32_t issuer = ptx::elect_one();
             int stage = 0;
             uint32_t phase = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                t2_wait_remote(&tmem_empty[acc], acc_phase ^ 1, pp.spin);
+                if (lane == 0) t2_wait_remote(&tmem_empty[acc], acc_phase ^ 1, pp.spin);
+                __syncwarp();
                 ptx::tc_fence_after();
                 const uint32_t d1 = tmem_base + static_cast<uint32_t>(acc * 2 * kTwBN);
                 const uint32_t d2 = d1 + kTwBN;
                 for (int kb = 0; kb < KB; ++kb) {
                     // 8 arrivals: each squarer warp of either CTA saw its own stage land (and, first time, its resident
                     // operands) and finished writing the squared copy
-                    t2_wait_remote(&sq_bar[stage], phase, pp.spin);
+                    if (lane == 0) t2_wait_remote(&sq_bar[stage], phase, pp.spin);
+                    __syncwarp();
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(sA + static_cast<size_t>(stage) * kTwStageA);
-                    const uint32_t ba_addr = ptx::smem_u32(sBa + static_cast<size_t>(kb) * kT2BBlock);
-                    const uint32_t bw_addr = ptx::smem_u32(sBw + static_cast<size_t>(kb) * kT2BBlock);
+                    const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + static_cast<size_t>(stage) * kTwStageA));
+                    const uint64_t ba_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sBa + static_cast<size_t>(kb) * kT2BBlock));
+                    const uint64_t bw_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sBw + static_cast<size_t>(kb) * kT2BBlock));
                     const uint32_t a2_tmem = tmem_base + kTwSqBase + stage * kTwSqCols;
+                    const uint32_t acc0 = kb != 0 ? 1u : 0u;
+                    if (issuer) {
+                        // a k-step of 16 elements = 32 bytes = 2 in the descriptor's (address >> 4) field
+                        if (!(SKY_DBG(p) & 8)) {
 #pragma unroll
-                    for (int k = 0; k < kKBlock / 16; ++k) {
-                        ptx::umma2_bf16(d1, ptx::make_sw128_kmajor_desc(a_addr + k * 32), ptx::make_sw128_kmajor_desc(ba_addr + k * 32),
-                                        idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (!(SKY_DBG(p) & 2)) ptx::umma2_bf16_ts(d2, a2_tmem + k * 8, ptx::make_sw128_kmajor_desc(bw_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < kKBlock / 16; ++k) ptx::umma2_bf16(d1, a_desc + 2 * k, ba_desc + 2 * k, idesc, k ? 1u : acc0);
+                        }
+                        if (!(SKY_DBG(p) & 2)) {
+#pragma unroll
+                            for (int k = 0; k < kKBlock / 16; ++k) ptx::umma2_bf16_ts(d2, a2_tmem + k * 8, bw_desc + 2 * k, idesc, k ? 1u : acc0);
+                        }
+                        ptx::umma2_commit_mc(&empty_bar[stage], 0b11);      // both producers may refill the stage
+                        if (kb == KB - 1) ptx::umma2_commit_mc(&tmem_full[acc], 0b11);   // both epilogues may read
                     }
-                    ptx::umma2_commit_mc(&empty_bar[stage], 0b11);      // both producers may refill the stage
+                    __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma2_commit_mc(&tmem_full[acc], 0b11);            // both epilogues may read their accumulators
             }
         }
     } else if (warp >= kT2EpiWarp0 && warp < kT2EpiWarp0 + 4) {
@@ -725,7 +736,7 @@ int launch_tc_weighted(sky_bank* b, const float* t, const float* w, int Q, int m
             pp.w.bank_policy = env_knob("SKY_TW2_POLICY", 0) == 1 ? ptx::kEvictFirst : 0x1000000000000000ull;   // evict-normal, as K2b's bank boxes
             pp.stages = stages2;
             { const int e = env_knob("SKY_TW2_STAGES", 0); if (e >= 2 && e < stages2) pp.stages = e; }
-            pp.spin = env_knob("SKY_TW2_SPIN", 1);
+            pp.spin = env_knob("SKY_TW2_SPIN", 0);      // measured: polling with back-off beats spinning (0.346 vs 0.374 ms)
             if (env_knob("SKY_TW2_OCC", 0)) {
                 int ncl = -1;
                 cudaLaunchConfig_t cfg = {};

@@ -95,3 +95,112 @@ def resident_simsearch(bank, target_latent, ra_decs, samples=None, num_extra_tok
         best_samples = samples[safe.cpu()]
         best_samples[~ok.cpu()] = 0
     return best_samples, idx, best_ra, scores
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# target side: mae_latent with target augmentation, latents kept on the device
+# ---------------------------------------------------------------------------------------------------------------
+class _RandomBrightness:
+    """img * U(lo, hi) -- reference utils/dataloaders.py:13-24"""
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi = lo, hi
+
+    def __call__(self, img):
+        import random
+        return img * random.uniform(self.lo, self.hi)
+
+
+class _RandomNoise:
+    """img + randn * U(lo, hi) -- reference utils/dataloaders.py:26-37"""
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi = lo, hi
+
+    def __call__(self, img):
+        import random
+        return img + torch.randn_like(img) * random.uniform(self.lo, self.hi)
+
+
+class _RandomChannelNaN:
+    """0..max_channels random channels set to NaN -- reference utils/dataloaders.py:39-87 (on a copy: the reference
+    writes into its argument, which is always a fresh tensor there because the crop precedes it)."""
+
+    def __init__(self, max_channels):
+        self.max_channels = max_channels
+
+    def __call__(self, img):
+        import random
+        C = img.shape[-3]
+        if self.max_channels > C:
+            raise ValueError(f"max_channels must be less than or equal to the number of channels in the image. "
+                             f"Got {self.max_channels} for an image with {C} channels.")
+        out = img.clone()
+        if out.dim() == 3:
+            for c in random.sample(range(C), random.randint(0, self.max_channels)):
+                out[c] = torch.nan
+        else:
+            for b in range(out.shape[0]):
+                for c in random.sample(range(C), random.randint(0, self.max_channels)):
+                    out[b, c] = torch.nan
+        return out
+
+
+def get_augmentations(img_size=64, flip=True, crop=True, brightness=0.8, noise=0.01, nan_channels=2):
+    """The reference's augmentation pipeline (utils/dataloaders.py:90-106), same transforms and ranges, usable on CUDA
+    tensors: random flips, RandomResizedCrop(scale 0.8-1, ratio 0.9-1.1), brightness, noise, NaN channels."""
+    from torchvision.transforms import v2
+    t = []
+    if flip:
+        t += [v2.RandomHorizontalFlip(), v2.RandomVerticalFlip()]
+    if crop:
+        t.append(v2.RandomResizedCrop(size=(img_size, img_size), scale=(0.8, 1.0), ratio=(0.9, 1.1), antialias=True))
+    if brightness is not None:
+        t.append(_RandomBrightness(brightness, 1 / brightness))
+    if noise is not None:
+        t.append(_RandomNoise(0.0, noise))
+    if nan_channels is not None:
+        t.append(_RandomChannelNaN(nan_channels))
+    return v2.Compose(t)
+
+
+def mae_latent(model, dataloader, device, n_batches=None, return_images=False, verbose=1,
+               apply_augmentations=False, num_augmentations=16, remove_cls=True, augmentations=None):
+    """Mirror of the reference's ``mae_latent`` (utils/eval_fns.py:72-140), same arguments: every sample followed by
+    its ``num_augmentations`` augmented copies (:92-108), encoded batch by batch.  Differences, both on purpose:
+    the augmentations run on the DEVICE tensors, and latents / images stay on the device (the reference moves every
+    batch to the host, :132-134, and ``mae_simsearch`` moves the targets straight back).  ``augmentations`` overrides
+    the pipeline (e.g. a deterministic one in tests)."""
+    device = torch.device(device)
+    if n_batches is None:
+        n_batches = len(dataloader)
+    if verbose > 0:
+        print(f'Encoding {min(len(dataloader), n_batches)} batches...')
+    model.eval()
+    enc = model.module if hasattr(model, "module") else model
+    aug = (augmentations or get_augmentations()) if apply_augmentations else None
+    latents, images = [], []
+    with torch.no_grad():
+        for samples, _masks, ra_decs in dataloader:
+            samples = samples.to(device, non_blocking=True)
+            ra_decs = ra_decs.to(device, non_blocking=True)
+            if aug is not None:
+                rows, rds = [], []
+                for idx in range(samples.shape[0]):
+                    rows.append(samples[idx:idx + 1])
+                    rows += [aug(samples[idx]).unsqueeze(0) for _ in range(num_augmentations)]
+                    rds += [ra_decs[idx:idx + 1]] * (1 + num_augmentations)
+                samples, ra_decs = torch.cat(rows), torch.cat(rds)
+            latent, _, _ = enc.forward_features(samples, ra_dec=ra_decs, mask=None, reshape_out=False)
+            if getattr(enc, "attn_pool", False):
+                remove_cls = False
+            if remove_cls:
+                latent = latent[:, enc.num_extra_tokens:]
+            latents.append(latent.detach())
+            if return_images:
+                images.append(samples.detach())
+            if len(latents) >= n_batches:
+                break
+    if return_images:
+        return torch.cat(latents), torch.cat(images)
+    return torch.cat(latents)
