@@ -347,7 +347,7 @@ def run_search_workload(name, wl, args, dev, steps, warmup, strong, headline):
     import torch
     import torch.distributed as dist
     from sky_embeddings_b200 import _lib, synth
-    from sky_embeddings_b200.distributed import CandidateExchange, shard_range
+    from sky_embeddings_b200.distributed import make_exchange, shard_range
     from tests import torch_ref as TR
 
     rank, local, world = dist_env()
@@ -369,7 +369,8 @@ def run_search_workload(name, wl, args, dev, steps, warmup, strong, headline):
     w_host = w_dev.cpu().pin_memory() if w_dev is not None else None
     out_s_host = torch.empty((Q, k), dtype=torch.float32).pin_memory()
     out_i_host = torch.empty((Q, k), dtype=torch.int64).pin_memory()
-    xchg = CandidateExchange(Q, k, dev) if world > 1 else None
+    # candidate exchange: peer-memory push + flag-waiting merge (csrc/exchange.cu), or one NCCL all-gather + merge kernel
+    xchg = make_exchange(Q, k, dev, kind=args.exchange) if world > 1 else None
     largest = metric == "cosine"
 
     def local_search(t, w, out_s=None, out_i=None):
@@ -501,6 +502,7 @@ def run_search_workload(name, wl, args, dev, steps, warmup, strong, headline):
                "warmup": max(warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                "config": workload_config(name, wl, world, strong),
+               "exchange": (args.exchange if world > 1 else None),
                "value_definition": "Q / step time over the global (row-sharded) bank" if (strong or world == 1) else
                                    "N_gpus * Q / step time (query-over-1M-vector-shard searches/s, weak scaling)",
                "qps_global_bank": agg, "parity": parity, "clocks": sampler.summary((t_wall0, t_wall1)),
@@ -740,6 +742,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(PIXEL_WORKLOADS))
     ap.add_argument("--also", default="default", help="'default', 'none' or a comma list of workloads reported as sub-records")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: candidate exchange over peer memory (default) or one NCCL all-gather")
     ap.add_argument("--strong", action="store_true", help="N > 1: shard the workload's bank over the ranks (strong scaling)")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor", "batch", "generic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")

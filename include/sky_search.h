@@ -179,6 +179,28 @@ SKY_API int sky_merge_candidates_strided(const float* scores, const int64_t* idx
                                  int64_t stride_scores, int64_t stride_idx, int k_out, int metric,
                                  float* out_scores, int64_t* out_idx, int device, void* stream);
 
+/* ---- candidate exchange of a row-sharded search over peer memory (NVLink) -------------------------------------
+ * The reference's running top-k is a chunk-wise merge (utils/similarity.py:18-35), so a bank sharded by rows over the
+ * GPUs of one box needs one exchange per search: every rank's [Q, k] candidates to every rank, then the merge above.
+ * Instead of an NCCL all-gather in front of sky_merge_candidates_strided, every rank owns a buffer all peers map:
+ * sky_exchange_merge pushes the local block into every peer with plain stores + a per-query flag, then one CTA per
+ * query waits for its R flags and merges -- two kernels of this library on the search stream, no collective launch.
+ * Setup (once): create on every rank, exchange the 64-byte handles with any transport (torch.distributed
+ * all_gather), open.  All ranks must call sky_exchange_merge the same number of times (it is a collective).
+ * One process per GPU: sky_exchange_open (cudaIpc).  Several ranks in one process: sky_exchange_open_local. */
+typedef struct sky_exchange sky_exchange_t;
+SKY_API int sky_exchange_create(sky_exchange_t** x, int device, int rank, int world, int max_Q, int max_k);
+SKY_API int sky_exchange_handle_bytes(void);
+SKY_API int sky_exchange_handle(sky_exchange_t* x, void* h_handle);
+SKY_API int sky_exchange_open(sky_exchange_t* x, const void* h_handles /* [world][sky_exchange_handle_bytes()] */);
+SKY_API int sky_exchange_open_local(sky_exchange_t* x, void* const* peer_ptrs /* [world] device pointers */);
+SKY_API void* sky_exchange_local_ptr(sky_exchange_t* x);
+SKY_API int sky_exchange_destroy(sky_exchange_t* x);
+/* scores[Q,k] f32 / idx[Q,k] i64 (global indices, idx < 0 = empty slot): this rank's best-first candidates ->
+ * out_scores / out_idx [Q, k_out]: the global top-k_out, identical on every rank. */
+SKY_API int sky_exchange_merge(sky_exchange_t* x, const float* scores, const int64_t* idx, int Q, int k, int k_out,
+                       int metric, float* out_scores, int64_t* out_idx, void* stream);
+
 /* Timing of the dominant (scoring) kernel of each search with CUDA events recorded on the launch
  * stream right around it: enable, run searches, then read (#launches, total ms); read synchronises. */
 SKY_API int sky_profile_enable(sky_bank_t* bank, int enable);

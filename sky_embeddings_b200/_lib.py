@@ -50,6 +50,14 @@ SIGNATURES = {
     "sky_center_clip": (_i, [_vp, _i64, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _i, _vp]),
     "sky_merge_candidates": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sky_merge_candidates_strided": (_i, [_vp, _vp, _i, _i, _i, _i64, _i64, _i, _i, _vp, _vp, _i, _vp]),
+    "sky_exchange_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
+    "sky_exchange_handle_bytes": (_i, []),
+    "sky_exchange_handle": (_i, [_vp, _vp]),
+    "sky_exchange_open": (_i, [_vp, _vp]),
+    "sky_exchange_open_local": (_i, [_vp, _vp]),
+    "sky_exchange_local_ptr": (_vp, [_vp]),
+    "sky_exchange_destroy": (_i, [_vp]),
+    "sky_exchange_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sky_profile_enable": (_i, [_vp, _i]),
     "sky_profile_read": (_i, [_vp, C.POINTER(_i64), C.POINTER(C.c_double), _i]),
     "sky_launch_count": (_i64, [_i]),

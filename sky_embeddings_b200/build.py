@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libskysearch.so")
-SOURCES = ["api.cu", "bank.cu", "simt_search.cu", "stream_search.cu", "pixel_search.cu", "pixel_prep.cu", "tc_search.cu", "tc_batch.cu", "tc_weighted.cu", "merge.cu"]
+SOURCES = ["api.cu", "bank.cu", "simt_search.cu", "stream_search.cu", "pixel_search.cu", "pixel_prep.cu", "tc_search.cu", "tc_batch.cu", "tc_weighted.cu", "merge.cu", "exchange.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "--expt-relaxed-constexpr"]

@@ -278,6 +278,8 @@ __attribute__((visibility("default"))) int sky_debug_stream_stats(unsigned long 
 __attribute__((visibility("default"))) int sky_debug_tb_trace(long long* h_out, int n) { return debug_read_tb_trace(h_out, n); }
 
 __attribute__((visibility("default"))) int sky_debug_epi(unsigned long long* h_out) { return debug_read_epi(h_out); }
+
+__attribute__((visibility("default"))) int sky_debug_tw_trace(unsigned long long* h_out, int n) { return debug_read_tw_trace(h_out, n); }
 #endif
 
 int sky_profile_enable(sky_bank_t* b, int enable) {

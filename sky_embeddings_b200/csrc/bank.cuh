@@ -119,6 +119,7 @@ int debug_read_epi(unsigned long long* h_out);
 bool tc_weighted_supported(const sky_bank* b, int metric, bool weighted, int n_top);
 size_t tc_weighted_scratch_bytes(const sky_bank* b);
 int tc_weighted_grid(const sky_bank* b);
+int debug_read_tw_trace(unsigned long long* h_out, int n);
 int launch_tc_weighted(sky_bank* b, const float* t, const float* w, int Q, int metric, const SearchState& s, cudaStream_t st);
 
 // tc_batch.cu

@@ -51,12 +51,31 @@ __device__ __forceinline__ void tw_cp_async_16(uint32_t smem_dst, const void* gs
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "l"(policy) : "memory");
 }
 
+// Per-query pre-filter coefficients from the current thresholds (one thread per query; called by the epilogue warps
+// between the two barriers that end a tile, and once before the first tile).
+template <bool COS>
+__device__ __forceinline__ void tw_prefilter_coeffs(int q, int nq, const Sink& sink, const float* sQ1, const float* sQ2, float* sC) {
+    if (q >= nq) {                       // padding query: nothing passes
+        sC[q] = COS ? INFINITY : -INFINITY;
+        return;
+    }
+    const float th = lds_f32(sink.thr_f + q * 4);        // NaN = no threshold yet -> NaN coefficient -> everything passes
+    if (COS) {
+        const float t2 = th * sQ1[q];
+        const float c = t2 * fabsf(t2);
+        sC[q] = fmaf(-fabsf(c), 8e-6f, c);
+    } else {
+        const float b = th / sQ2[q] - sQ1[q];            // q2 = 1 / (D sum w) > 0
+        sC[q] = fmaf(fabsf(b) + fabsf(sQ1[q]), 8e-6f, b);
+    }
+}
+
 // Epilogue of one 128-row tile for one warp (thread = bank row = TMEM lane): D1 | D2 accumulators of 64 queries at
 // `taddr` -> conservative pre-filter bitmask -> exact score and insert of the survivors.  `release` runs once the
 // last accumulator chunk is in registers (the accumulator stage may then be overwritten by the next tile's MMAs).
 template <bool COS, typename Release>
 __device__ __forceinline__ void tw_score_tile(uint32_t taddr, uint32_t row, bool valid, int nq, int debug, const Sink& sink,
-                                              const float* sQ1, const float* sQ2, Release release) {
+                                              const float* sQ1, const float* sQ2, const float* sC, Release release) {
     constexpr bool largest = COS;
 #pragma unroll 1
     for (int c = 0; c < kTwBN / 32; ++c) {
@@ -74,30 +93,29 @@ __device__ __forceinline__ void tw_score_tile(uint32_t taddr, uint32_t row, bool
             // cosine: the accumulated w.(z o z) can round slightly below zero for a near-null row
             return COS ? __fdividef(d1, fmaf(q1, sqrtf(fmaxf(d2, 0.f)), 1e-6f)) : (q1 - 2.0f * d1 + d2) * q2;
         };
-        // FAST PATH: conservative pre-filter without square root or division.  Thresholds are read with vector
-        // loads and may be stale (they only tighten); NaN goes on to the exact test; padding queries never pass.
+        // FAST PATH (kept short: three warp roles share each scheduler's instruction cache, and a long unrolled
+        // epilogue slows the MMA issuer and the squarers down): a conservative pre-filter against per-query
+        // coefficients sC[q] that tw_prefilter_coeffs derives from the thresholds once per tile
         //   cosine: s >= th  <=>  d1 >= th (q1 sqrt(d2) + 1e-6); with f(x) = x |x| (monotone) this is implied by
-        //           f(d1 + 1e-6) >= f(th q1) d2, lowered by a few 1e-6 relative
-        //   MSE:    s <= th  <=>  (q1 - 2 d1 + d2) q2 <= th
+        //           f(d1 + 1e-6) >= f(th q1) d2;   sC = f(th q1), lowered by a few 1e-6 relative
+        //   MSE:    s <= th  <=>  (q1 - 2 d1 + d2) q2 <= th  <=>  d2 - 2 d1 <= th / q2 - q1 = sC (raised a little)
+        // sC may be a tile stale (thresholds only tighten); NaN (no threshold yet) passes everything on to the exact
+        // test; padding queries carry +-inf and never pass.
         uint32_t mbits = 0;
-        const uint32_t thf_addr = sink.thr_f + c * 32 * 4;
 #pragma unroll
         for (int g4 = 0; g4 < 8; ++g4) {
-            float th[4];
-            asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(th[0]), "=f"(th[1]), "=f"(th[2]), "=f"(th[3]) : "r"(thf_addr + g4 * 16) : "memory");
+            const float4 cq = *reinterpret_cast<const float4*>(sC + c * 32 + g4 * 4);
+            const float cc[4] = {cq.x, cq.y, cq.z, cq.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int j = g4 * 4 + u, q = c * 32 + j;
+                const int j = g4 * 4 + u;
                 const float d1 = __uint_as_float(v1[j]), d2 = __uint_as_float(v2[j]);
                 bool pass;
                 if (COS) {
-                    const float x = d1 + 1e-6f, t2 = th[u] * sQ1[q];
-                    float rhs = t2 * fabsf(t2) * fmaxf(d2, 0.f);
-                    rhs = fmaf(-fabsf(rhs), 8e-6f, rhs);
-                    pass = !(x * fabsf(x) < rhs);
+                    const float x = d1 + 1e-6f;
+                    pass = !(x * fabsf(x) < cc[u] * fmaxf(d2, 0.f));
                 } else {
-                    pass = !((sQ1[q] - 2.0f * d1 + d2) * sQ2[q] > th[u]);
+                    pass = !(fmaf(-2.0f, d1, d2) > cc[u]);
                 }
                 mbits |= (pass ? 1u : 0u) << j;
             }
@@ -141,7 +159,8 @@ tc_weighted_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     float* sQ1 = reinterpret_cast<float*>(sThr + kTwBN);
     float* sQ2 = sQ1 + kTwBN;
     float* sThrF = sQ2 + kTwBN;
-    int* sCnt = reinterpret_cast<int*>(sThrF + kTwBN);
+    float* sC = sThrF + kTwBN;                                                      // [64] pre-filter coefficients
+    int* sCnt = reinterpret_cast<int*>(sC + kTwBN);
     uint32_t* sLmax = reinterpret_cast<uint32_t*>(sCnt + kTwBN);
     uint32_t* sHist = sLmax + kTwBN;                                                // [4][256]
     uint32_t* sTmemBase = sHist + 4 * 256;
@@ -175,6 +194,7 @@ tc_weighted_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         sThrF[q] = (q < p.nq) ? __uint_as_float(0x7FC00000u) : (largest ? INFINITY : -INFINITY);
         sQ1[q] = p.qc1[q];
         sQ2[q] = p.qc2[q];
+        sC[q] = (q < p.nq) ? __uint_as_float(0x7FC00000u) : (largest ? INFINITY : -INFINITY);
         sCnt[q] = 0;
         sLmax[q] = 0;
     }
@@ -302,10 +322,11 @@ tc_weighted_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             __syncwarp();
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 2 * kTwBN);
-            tw_score_tile<COS>(taddr, static_cast<uint32_t>(row), valid, p.nq, SKY_DBG(p), sink, sQ1, sQ2,
+            tw_score_tile<COS>(taddr, static_cast<uint32_t>(row), valid, p.nq, SKY_DBG(p), sink, sQ1, sQ2, sC,
                                [&]() { if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]); });
             ptx::named_bar_sync(1, 128);
             sink_prune_if_full(sink, p.nq, e, 4, hist);
+            if (e * 32 + lane < kTwBN) tw_prefilter_coeffs<COS>(e * 32 + lane, p.nq, sink, sQ1, sQ2, sC);
             ptx::named_bar_sync(1, 128);
             if (e == 0 && lane == 0) *sTilesDone = it + 1;
         }
@@ -365,6 +386,18 @@ constexpr int kT2HalfN = kTwBN / 2;              // query rows resident per CTA
 constexpr int kT2BBlock = kT2HalfN * 128;        // 4 KB: one k-block of one operand half
 constexpr int kT2MaxStages = 8;                  // TMEM: 256 accumulator columns + 32 per stage <= 512
 
+// experiment builds: timeline of cluster 0 (rows: 0 TMA issue, 1 squarer saw full (warp 0), 2 squarer arrived, 3 MMA saw
+// sq_bar, 4 MMA committed, 5 MMA got tmem_empty (per tile), 6 epilogue saw tmem_full, 7 epilogue released, 8 epilogue tile
+// done; the odd CTA writes rows 9.. the same way), SKY_TW_DEBUG bit 5
+#ifdef SKY_EXPERIMENTS
+constexpr int kTwTraceLen = 1024;
+constexpr int kTwTraceRows = 9;
+__device__ unsigned long long g_tw_trace[2 * kTwTraceRows * kTwTraceLen];
+#define TW_TRACE(row, i) do { if ((SKY_DBG(p) & 32) && blockIdx.x < 2 && (i) < kTwTraceLen) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_tw_trace[(blockIdx.x * kTwTraceRows + (row)) * kTwTraceLen + (i)] = t_; } } while (0)
+#else
+#define TW_TRACE(row, i) do { } while (0)
+#endif
+
 struct Tw2Params {
     TwParams w;
     int stages;
@@ -397,7 +430,8 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
     float* sQ1 = reinterpret_cast<float*>(sThr + kTwBN);
     float* sQ2 = sQ1 + kTwBN;
     float* sThrF = sQ2 + kTwBN;
-    int* sCnt = reinterpret_cast<int*>(sThrF + kTwBN);
+    float* sC = sThrF + kTwBN;                                                      // [64] pre-filter coefficients
+    int* sCnt = reinterpret_cast<int*>(sC + kTwBN);
     uint32_t* sLmax = reinterpret_cast<uint32_t*>(sCnt + kTwBN);
     uint32_t* sHist = sLmax + kTwBN;                                                // [4][256]
     uint32_t* sTmemBase = sHist + 4 * 256;
@@ -434,6 +468,7 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
         sThrF[q] = (q < p.nq) ? __uint_as_float(0x7FC00000u) : (largest ? INFINITY : -INFINITY);
         sQ1[q] = p.qc1[q];
         sQ2[q] = p.qc2[q];
+        sC[q] = (q < p.nq) ? __uint_as_float(0x7FC00000u) : (largest ? INFINITY : -INFINITY);
         sCnt[q] = 0;
         sLmax[q] = 0;
     }
@@ -462,6 +497,7 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
                 const int tile = min(tile_of(it), p.num_tiles - 1);
                 for (int kb = 0; kb < KB; ++kb) {
                     t2_wait_remote(&empty_bar[stage], phase ^ 1, pp.spin);
+                    TW_TRACE(0, it * KB + kb);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], kTwStageA);
                     ptx::tma_load_2d(&tmap_bank, sA + static_cast<size_t>(stage) * kTwStageA, &full_bar[stage], 0,
                                      (tile * KB + kb) * kTileRows, p.bank_policy);
@@ -482,6 +518,7 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
         if (total > 0) ptx::mbar_wait_relaxed(b_full, 0, 64);    // the first sq_bar arrival also vouches for the resident operands
         for (int i = 0; i < total; ++i) {
             ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);
+            if (quarter == 0 && lane == 0) TW_TRACE(1, i);
             if (SKY_DBG(p) & 1) {      // experiment: no squaring, only the hand-off
                 __syncwarp();
                 if (lane == 0) { if (rank == 0) ptx::mbar_arrive(&sq_bar[stage]); else ptx::mbar_arrive_cluster(&sq_bar[stage], 0); }
@@ -507,6 +544,7 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
             if (lane == 0) {
                 if (rank == 0) ptx::mbar_arrive(&sq_bar[stage]);
                 else ptx::mbar_arrive_cluster(&sq_bar[stage], 0);
+                if (quarter == 0) TW_TRACE(2, i);
             }
             if (++stage == S) { stage = 0; phase ^= 1; }
         }
@@ -521,7 +559,7 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
             for (int it = 0; it < my_tiles; ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                if (lane == 0) t2_wait_remote(&tmem_empty[acc], acc_phase ^ 1, pp.spin);
+                if (lane == 0) { t2_wait_remote(&tmem_empty[acc], acc_phase ^ 1, pp.spin); TW_TRACE(5, it); }
                 __syncwarp();
                 ptx::tc_fence_after();
                 const uint32_t d1 = tmem_base + static_cast<uint32_t>(acc * 2 * kTwBN);
@@ -529,7 +567,7 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
                 for (int kb = 0; kb < KB; ++kb) {
                     // 8 arrivals: each squarer warp of either CTA saw its own stage land (and, first time, its resident
                     // operands) and finished writing the squared copy
-                    if (lane == 0) t2_wait_remote(&sq_bar[stage], phase, pp.spin);
+                    if (lane == 0) { t2_wait_remote(&sq_bar[stage], phase, pp.spin); TW_TRACE(3, it * KB + kb); }
                     __syncwarp();
                     ptx::tc_fence_after();
                     const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + static_cast<size_t>(stage) * kTwStageA));
@@ -549,6 +587,7 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
                         }
                         ptx::umma2_commit_mc(&empty_bar[stage], 0b11);      // both producers may refill the stage
                         if (kb == KB - 1) ptx::umma2_commit_mc(&tmem_full[acc], 0b11);   // both epilogues may read
+                        TW_TRACE(4, it * KB + kb);
                     }
                     __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1; }
@@ -565,20 +604,22 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
             const uint32_t acc_phase = (it >> 1) & 1;
             const int64_t row = static_cast<int64_t>(tile_of(it)) * kTileRows + quarter * 32 + lane;
             const bool valid = row < p.rows;
-            if (lane == 0) { if (pp.spin) ptx::mbar_wait(&tmem_full[acc], acc_phase); else ptx::mbar_wait_relaxed(&tmem_full[acc], acc_phase, 128); }
+            if (lane == 0) { if (pp.spin) ptx::mbar_wait(&tmem_full[acc], acc_phase); else ptx::mbar_wait_relaxed(&tmem_full[acc], acc_phase, 128); if (e == 0) TW_TRACE(6, it); }
             __syncwarp();
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 2 * kTwBN);
-            tw_score_tile<COS>(taddr, static_cast<uint32_t>(row), valid, p.nq, SKY_DBG(p), sink, sQ1, sQ2, [&]() {
+            tw_score_tile<COS>(taddr, static_cast<uint32_t>(row), valid, p.nq, SKY_DBG(p), sink, sQ1, sQ2, sC, [&]() {
                 if (lane == 0) {
                     if (rank == 0) ptx::mbar_arrive(&tmem_empty[acc]);
                     else ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+                    if (e == 0) TW_TRACE(7, it);
                 }
             });
             ptx::named_bar_sync(1, 128);
             sink_prune_if_full(sink, p.nq, e, 4, hist);
+            if (e * 32 + lane < kTwBN) tw_prefilter_coeffs<COS>(e * 32 + lane, p.nq, sink, sQ1, sQ2, sC);
             ptx::named_bar_sync(1, 128);
-            if (e == 0 && lane == 0) *sTilesDone = it + 1;
+            if (e == 0 && lane == 0) { *sTilesDone = it + 1; TW_TRACE(8, it); }
         }
         ptx::named_bar_sync(1, 128);
         for (int q = e * 32 + lane; q < p.nq; q += 128) {
@@ -615,6 +656,15 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
         ptx::tmem_dealloc2(tmem_base, 512);
     }
 }
+
+#ifdef SKY_EXPERIMENTS
+int debug_read_tw_trace(unsigned long long* h_out, int n) {
+    if (n > 2 * kTwTraceRows * kTwTraceLen) n = 2 * kTwTraceRows * kTwTraceLen;
+    SKY_CUDA(cudaDeviceSynchronize());
+    SKY_CUDA(cudaMemcpyFromSymbol(h_out, g_tw_trace, sizeof(unsigned long long) * n));
+    return SKY_OK;
+}
+#endif
 
 // a = w o t and w as bf16 operand matrices [64, Dp] (zero padded) + per-query constants
 __global__ void pack_weighted_kernel(const float* __restrict__ t, const float* __restrict__ w, int nq, int D, int Dp, int metric,
@@ -663,7 +713,7 @@ size_t tc_weighted_scratch_bytes(const sky_bank* b) {
 }
 
 static size_t tw2_tail_bytes() {
-    return (3 * kT2MaxStages + 1 + 4) * sizeof(uint64_t) + 16 + kTwBN * (8 + 5 * 4) + 4 * 256 * 4 + 16;
+    return (3 * kT2MaxStages + 1 + 4) * sizeof(uint64_t) + 16 + kTwBN * (8 + 6 * 4) + 4 * 256 * 4 + 16;
 }
 
 // ring depth of the CTA-pair kernel (0 = the resident query halves do not leave room for a useful ring)
@@ -699,7 +749,7 @@ int launch_tc_weighted(sky_bank* b, const float* t, const float* w, int Q, int m
     const bool pair = tw2_usable(b) && (s.P % 2) == 0;
     const int stages2 = pair ? tw2_stages(b->Dp) : 0;
     const size_t smem = pair ? 1024 + static_cast<size_t>(b->Dp / kKBlock) * 2 * kT2BBlock + static_cast<size_t>(stages2) * kTwStageA + tw2_tail_bytes()
-                             : 1024 + static_cast<size_t>(kTwStages) * kTwStage + (3 * kTwStages + 4) * 8 + kTwBN * (8 + 5 * 4) + 4 * 256 * 4 + 64;
+                             : 1024 + static_cast<size_t>(kTwStages) * kTwStage + (3 * kTwStages + 4) * 8 + kTwBN * (8 + 6 * 4) + 4 * 256 * 4 + 64;
     if (pair) {
         if (metric == SKY_COSINE) SKY_CUDA(cudaFuncSetAttribute(tc_weighted2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         else SKY_CUDA(cudaFuncSetAttribute(tc_weighted2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -86,6 +86,79 @@ class CandidateExchange:
         return self.out_scores, self.out_idx
 
 
+class PeerExchange:
+    """The exchange step over PEER MEMORY instead of a collective: every rank's candidate block is pushed into a
+    buffer of every peer with plain NVLink stores and a per-query flag, and the merge kernel waits for its flags
+    (csrc/exchange.cu).  torch.distributed is used once, at construction, to trade the 64-byte cudaIpc handles.
+    Same interface as CandidateExchange: write the local candidates into .scores / .idx, call merge()."""
+
+    def __init__(self, Q, k, device, group=None):
+        import ctypes as C
+        from . import _lib as L
+        self.Q, self.k, self.group = int(Q), int(k), group
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PeerExchange needs CUDA devices with peer access: there is no CPU fallback")
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lib = L.load()
+        self._h = C.c_void_p()
+        L.check(lib.sky_exchange_create(C.byref(self._h), self.device.index or 0, self.rank, self.world, self.Q, self.k))
+        if self.world > 1:
+            nb = lib.sky_exchange_handle_bytes()
+            mine = (C.c_ubyte * nb)()
+            L.check(lib.sky_exchange_handle(self._h, mine))
+            local = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+            every = torch.empty(self.world * nb, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, local, group=group)
+            blob = bytes(every.cpu().tolist())
+            L.check(lib.sky_exchange_open(self._h, blob))
+            dist.barrier(group=group)                  # nobody pushes before every peer has mapped every buffer
+        self.scores = torch.empty((self.Q, self.k), dtype=torch.float32, device=self.device)
+        self.idx = torch.empty((self.Q, self.k), dtype=torch.int64, device=self.device)
+        self.out_scores = torch.empty((self.Q, self.k), dtype=torch.float32, device=self.device)
+        self.out_idx = torch.empty((self.Q, self.k), dtype=torch.int64, device=self.device)
+
+    def merge(self, metric):
+        import ctypes as C
+        from . import _lib as L
+        from .engine import _stream
+        if self.world == 1:
+            return self.scores, self.idx
+        L.check(L.load().sky_exchange_merge(
+            self._h, C.c_void_p(self.scores.data_ptr()), C.c_void_p(self.idx.data_ptr()), self.Q, self.k, self.k,
+            L.METRICS["cosine" if metric == "cosine" else "MSE"], C.c_void_p(self.out_scores.data_ptr()),
+            C.c_void_p(self.out_idx.data_ptr()), _stream(self.device)))
+        return self.out_scores, self.out_idx
+
+    def close(self):
+        if getattr(self, "_h", None):
+            from . import _lib as L
+            torch.cuda.synchronize(self.device)
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)         # peers may still be reading what this rank maps
+            L.load().sky_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                from . import _lib as L
+                L.load().sky_exchange_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def make_exchange(Q, k, device, group=None, kind="peer"):
+    """kind: 'peer' (NVLink stores + flags, csrc/exchange.cu) or 'nccl' (one all-gather + merge kernel)."""
+    if kind == "peer":
+        return PeerExchange(Q, k, device, group)
+    if kind == "nccl":
+        return CandidateExchange(Q, k, device, group)
+    raise ValueError(f"unknown exchange kind {kind!r}")
+
+
 def sharded_search(local_search, k, metric, merge=None, group=None):
     """local_search() -> (scores [Q, k], idx [Q, k] with GLOBAL indices) on this rank's shard.
     Returns the global top-k on every rank.  `merge` defaults to the CUDA merge kernel."""
@@ -101,15 +174,18 @@ def sharded_search(local_search, k, metric, merge=None, group=None):
 class ShardedBank:
     """A Bank holding rows [row_lo, row_hi) of a global bank of n_total items."""
 
-    def __init__(self, bank, row_lo, n_total, group=None):
+    def __init__(self, bank, row_lo, n_total, group=None, exchange="peer"):
         self.bank, self.row_lo, self.n_total, self.group = bank, int(row_lo), int(n_total), group
+        self.exchange = exchange
         self._xchg = None
 
     def search(self, t, w=None, k=100, metric="cosine", combine="min", n_top_sims=None, path="auto"):
         if dist.is_initialized() and dist.get_world_size(self.group) > 1 and t.is_cuda:
             Q = 1 if t.dim() == 1 else t.shape[0]
             if self._xchg is None or (self._xchg.Q, self._xchg.k) != (Q, k):
-                self._xchg = CandidateExchange(Q, k, self.bank.device, self.group)
+                if self._xchg is not None and hasattr(self._xchg, "close"):
+                    self._xchg.close()
+                self._xchg = make_exchange(Q, k, self.bank.device, self.group, self.exchange)
             x = self._xchg
             self.bank.search(t, w, k, metric, combine, n_top_sims, path, idx_offset=self.row_lo,
                              out_scores=x.scores, out_idx=x.idx)

@@ -73,3 +73,15 @@ def test_two_rank_gloo_sharded_search_equals_global():
         # a shard shorter than k: padding (-1) must not leak into the merged result
         mp.spawn(_worker, args=(world, _free_port(), 50, 16, 3, 30, "MSE", out2), nprocs=world, join=True)
         assert dict(out2) == {0: True, 1: True}
+
+
+def test_peer_exchange_needs_cuda():
+    """The peer-memory exchange has no CPU path: constructing it on the CPU raises (the gloo tests above cover the
+    collective-based host logic)."""
+    import pytest
+    import torch
+    from sky_embeddings_b200.distributed import PeerExchange, make_exchange
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PeerExchange(4, 10, torch.device("cpu"))
+    with pytest.raises(ValueError):
+        make_exchange(4, 10, torch.device("cpu"), kind="smoke-signals")
