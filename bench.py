@@ -509,7 +509,7 @@ def run_search_workload(name, wl, args, dev, steps, warmup, strong, headline):
                "e2e": {"value": (Q if (strong or world == 1) else world * Q) / (e2e_step * 1e-3), "unit": "queries/s",
                        "ms_per_step": e2e_step, "h2d_bytes_per_step": t_host.numel() * 4 * (2 if weighted else 1),
                        "d2h_bytes_per_step": Q * k * 12,
-                       "api": "sky_search_host (C ABI, pinned host buffers)" if world == 1 else
+                       "api": "sky_search_host (C ABI, pinned host buffers: queries read and results written over PCIe by the kernels themselves, inside the timed call)" if world == 1 else
                               "pinned H2D + sky_search + candidate exchange + merge + D2H"},
                "gpu_launches": launches, "gpu_launches_per_step": launches / steps, "env_knobs": active_knobs()}
         if kernel == "batch":

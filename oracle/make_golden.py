@@ -325,6 +325,29 @@ def cli_cases(ref):
     return out
 
 
+def c1_real_cases(ref):
+    """BASELINE config 1 with the reference's OWN encoder: utils/mim_vit.py (unmodified, behind the test-only timm shim,
+    tests/ref_encoder.py), random-init `mim_1` (seed 0), 1k target cutouts, 10k bank cutouts, cosine top-10 on the CPU
+    through the reference's mae_simsearch exactly as similarity_search.py:169-171 calls it (use_weights=True)."""
+    from tests.ref_encoder import build_mim1
+    from tests.stub_encoder import CutoutLoader, c1_inputs
+    out = {}
+    bank, tgt, anchors = c1_inputs()
+    model, _ = build_mim1("cpu", seed=0)
+    with torch.no_grad():
+        target_latent = torch.cat([model.module.forward_features(torch.from_numpy(tgt[s:s + 100]), reshape_out=False)[0]
+                                   for s in range(0, len(tgt), 100)])
+    out["checksum"] = np.array(checksum(bank[:64], tgt[:8]))
+    out["anchors"] = anchors
+    out["target_latent_sum"] = target_latent.double().sum(dim=(1, 2)).numpy()[:16]
+    for mp, name in ((True, "maxpool"), (False, "patches")):
+        res = quiet(ref.mae_simsearch, model, target_latent, CutoutLoader(bank, 64), "cpu", metric="cosine", combine="min",
+                    use_weights=True, max_pool=mp, cls_token=False, nested_batches=False, n_save=10)
+        out[f"scores.{name}"] = res[3].numpy()
+        out[f"idx.{name}"] = res[2][:, 0].numpy().astype(np.int64)
+    return out
+
+
 def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -334,10 +357,11 @@ def main():
     for name, fn in (("simsearch_small", simsearch_cases), ("simsearch_mim1_shape", mim1_shape_case),
                      ("short_bank", short_bank_case), ("compute_similarity", compute_similarity_cases),
                      ("update_best", update_best_cases), ("pixel_small", pixel_cases), ("c1_mim1_stub", c1_cases),
-                     ("ingest", ingest_cases), ("cli_small", cli_cases)):
+                     ("ingest", ingest_cases), ("cli_small", cli_cases),
+                     ("c1_mim1_real", c1_real_cases)):
         if only and name not in only:
             continue
-        if name == "c1_mim1_stub":
+        if name in ("c1_mim1_stub", "c1_mim1_real"):
             torch.set_num_threads(os.cpu_count() or 1)      # the encoder pass over 11k cutouts
         data = fn(ref)
         path = os.path.join(OUT, name + ".npz")

@@ -465,6 +465,28 @@ int sky_search_host(sky_bank_t* b, const float* h_t, const float* h_w, int Q, in
     const size_t qb = static_cast<size_t>(Q) * b->D * sizeof(float);
     const size_t sb = static_cast<size_t>(Q) * k * sizeof(float);
     const size_t ib = static_cast<size_t>(Q) * k * sizeof(int64_t);
+    // Pinned (page-locked, mapped) host buffers are read and written by the kernels directly: the packing kernel pulls
+    // the queries over PCIe and the merge kernel posts the [Q, k] result rows to the host, so the call is the search's
+    // own launches plus one stream synchronisation -- no staging copies (four copy operations and their launch gaps,
+    // ~40 us of a 0.3 ms BASELINE config 2 step).  Pageable buffers take the staged route below.
+    {
+        auto mapped = [](const void* h) -> void* {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+        };
+        void* m_t = mapped(h_t);
+        void* m_w = h_w ? mapped(h_w) : nullptr;
+        void* m_s = mapped(h_out_scores);
+        void* m_i = mapped(h_out_idx);
+        if (m_t && (m_w || !h_w) && m_s && m_i) {
+            int rc0 = search_impl(b, static_cast<const float*>(m_t), static_cast<const float*>(m_w), Q, metric, combine, n_top_sims, k,
+                                  idx_offset, static_cast<float*>(m_s), static_cast<int64_t*>(m_i), path, st);
+            if (rc0) return rc0;
+            SKY_CUDA(cudaStreamSynchronize(st));
+            return SKY_OK;
+        }
+    }
     // staging lives behind the tensor-path scratch in ws2
     size_t scratch = tc_scratch_bytes(b, Q);
     if (tc_weighted_scratch_bytes(b) > scratch) scratch = tc_weighted_scratch_bytes(b);
@@ -567,16 +589,18 @@ static int pixel_impl(sky_bank_t* b, const float* q, const unsigned char* qmask,
     if (!b->pixel) return set_error(SKY_ERR_STATE, "not a pixel bank");
     if (Q < 1) return set_error(SKY_ERR_ARG, "Q must be positive");
     const int64_t nq = static_cast<int64_t>(Q) * b->D;
-    int rc = ensure_ws2(b, static_cast<size_t>(nq) * sizeof(float) + 256);
+    const size_t qp_bytes = static_cast<size_t>(round_up(nq * static_cast<int64_t>(sizeof(float)), 256));
+    int rc = ensure_ws2(b, qp_bytes + static_cast<size_t>(Q) * sizeof(int) + 256);
     if (rc) return rc;
     float* qp = reinterpret_cast<float*>(b->ws2);
-    rc = launch_pixel_fold(q, qmask, nq, qp, st);
+    int* excl = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(b->ws2) + qp_bytes);   // per query: pixels excluded?
+    rc = launch_pixel_fold(q, qmask, nq, b->D, qp, excl, st);
     if (rc) return rc;
     const int qc = pixel_pick_qc(Q);
     SearchState s{};
     if (emit) {
         if (n_items == 0) return SKY_OK;
-        return launch_pixel_search(b, qp, Q, item0, item0 + n_items, s, pixel_grid(b, n_items), qc, emit, st);
+        return launch_pixel_search(b, qp, excl, Q, item0, item0 + n_items, s, pixel_grid(b, n_items), qc, emit, st);
     }
     const int grid = pixel_grid(b, b->rows);
     rc = plan_state(b, grid, Q, k, grid, &s);
@@ -584,7 +608,7 @@ static int pixel_impl(sky_bank_t* b, const float* q, const unsigned char* qmask,
     rc = launch_init_state(s, grid, st);
     if (rc) return rc;
     if (b->rows > 0) {
-        rc = launch_pixel_search(b, qp, Q, 0, b->rows, s, grid, qc, nullptr, st);
+        rc = launch_pixel_search(b, qp, excl, Q, 0, b->rows, s, grid, qc, nullptr, st);
         if (rc) return rc;
     }
     return launch_merge_lists(s, SKY_MSE, idx_offset, out_scores, out_idx, st);

@@ -94,9 +94,9 @@ int launch_stream_search(const sky_bank* b, const SimtArgs& a, const SearchState
 // pixel_search.cu
 int pixel_pick_qc(int Q);
 int pixel_grid(const sky_bank* b, int64_t n_rows);
-int launch_pixel_fold(const float* q, const unsigned char* mask, int64_t n, float* qp, cudaStream_t st);
-int launch_pixel_search(const sky_bank* b, const float* qp, int Q, int64_t row_lo, int64_t row_hi, const SearchState& s,
-                        int grid, int qc, float* emit, cudaStream_t st);
+int launch_pixel_fold(const float* q, const unsigned char* mask, int64_t n, int D, float* qp, int* excl, cudaStream_t st);
+int launch_pixel_search(const sky_bank* b, const float* qp, const int* excl, int Q, int64_t row_lo, int64_t row_hi,
+                        const SearchState& s, int grid, int qc, float* emit, cudaStream_t st);
 
 // pixel_prep.cu
 int launch_snr(const float* img, int64_t n_items, int C, int H, int W, int n_central, int n_min_channels, float* out_snr,

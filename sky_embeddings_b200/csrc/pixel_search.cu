@@ -37,6 +37,7 @@ constexpr int kPxMaxStages = 13;
 struct PixelParams {
     const unsigned char* bank;   // [rows][D] fp32, row-major
     const float* qp;             // [Q][D] folded queries (NaN = pixel excluded)
+    const int* excl;             // [Q] != 0: the folded query excludes pixels (mask or NaN); 0 = every pixel takes part
     int64_t row_lo, row_hi;
     int D, nch;                  // pieces per row
     int q0, nq;
@@ -48,12 +49,14 @@ struct PixelParams {
 };
 
 // q' = q where (mask != 0 and q is not NaN), NaN elsewhere
-__global__ void pixel_fold_query_kernel(const float* __restrict__ q, const unsigned char* __restrict__ mask, int64_t n,
-                                        float* __restrict__ qp) {
+__global__ void pixel_fold_query_kernel(const float* __restrict__ q, const unsigned char* __restrict__ mask, int64_t n, int D,
+                                        float* __restrict__ qp, int* __restrict__ excl) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float v = q[i];
-    qp[i] = (mask == nullptr || mask[i] != 0) ? v : __uint_as_float(0x7FC00000u);
+    const float f = (mask == nullptr || mask[i] != 0) ? v : __uint_as_float(0x7FC00000u);
+    qp[i] = f;
+    if (f != f) atomicOr(excl + i / D, 1);      // rare: one flag per query, read by the search kernel
 }
 
 __device__ __forceinline__ void px_bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
@@ -85,6 +88,10 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
     const int my_groups = (n_groups > static_cast<int64_t>(blockIdx.x))
                               ? static_cast<int>((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     const int last_len = p.D - (p.nch - 1) * kPxChunkElems;      // elements in the last piece of a row
+    // every query of this pass compares all its pixels (no mask, no NaN): the pixel's validity then depends on the bank
+    // alone, one test and one count per pixel serve all queries of the pass
+    bool clean = true;
+    for (int q = 0; q < p.nq; ++q) clean = clean && (__ldg(p.excl + p.q0 + q) == 0);
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], kPxWarps); }
@@ -183,18 +190,39 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                          : "=f"(xv[j].x), "=f"(xv[j].y), "=f"(xv[j].z), "=f"(xv[j].w) : "r"(src + j * 512));
                         }
-#pragma unroll
-                        for (int q = 0; q < QC; ++q)
+                        if (clean) {
+                            // 2 instructions per pixel and query (subtract, predicated multiply-add) + a test and a
+                            // count per pixel, instead of 4 per pixel and query
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float d0 = qv[q][j].x - xv[j].x, d1 = qv[q][j].y - xv[j].y;
-                                const float d2 = qv[q][j].z - xv[j].z, d3 = qv[q][j].w - xv[j].w;
-                                // NaN (either side missing or masked out) drops out of both sums
-                                if (d0 == d0) { acc[r][q] = fmaf(d0, d0, acc[r][q]); cnt[r][q] += 1; }
-                                if (d1 == d1) { acc[r][q] = fmaf(d1, d1, acc[r][q]); cnt[r][q] += 1; }
-                                if (d2 == d2) { acc[r][q] = fmaf(d2, d2, acc[r][q]); cnt[r][q] += 1; }
-                                if (d3 == d3) { acc[r][q] = fmaf(d3, d3, acc[r][q]); cnt[r][q] += 1; }
+                                const bool in = e0 + j * 128 < len;      // a short last piece: stale ring data beyond it
+                                const bool p0 = in && xv[j].x == xv[j].x, p1 = in && xv[j].y == xv[j].y;
+                                const bool p2 = in && xv[j].z == xv[j].z, p3 = in && xv[j].w == xv[j].w;
+                                cnt[r][0] += (p0 ? 1 : 0) + (p1 ? 1 : 0) + (p2 ? 1 : 0) + (p3 ? 1 : 0);
+#pragma unroll
+                                for (int q = 0; q < QC; ++q) {
+                                    const float d0 = qv[q][j].x - xv[j].x, d1 = qv[q][j].y - xv[j].y;
+                                    const float d2 = qv[q][j].z - xv[j].z, d3 = qv[q][j].w - xv[j].w;
+                                    if (p0) acc[r][q] = fmaf(d0, d0, acc[r][q]);
+                                    if (p1) acc[r][q] = fmaf(d1, d1, acc[r][q]);
+                                    if (p2) acc[r][q] = fmaf(d2, d2, acc[r][q]);
+                                    if (p3) acc[r][q] = fmaf(d3, d3, acc[r][q]);
+                                }
                             }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < QC; ++q)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float d0 = qv[q][j].x - xv[j].x, d1 = qv[q][j].y - xv[j].y;
+                                    const float d2 = qv[q][j].z - xv[j].z, d3 = qv[q][j].w - xv[j].w;
+                                    // NaN (either side missing or masked out) drops out of both sums
+                                    if (d0 == d0) { acc[r][q] = fmaf(d0, d0, acc[r][q]); cnt[r][q] += 1; }
+                                    if (d1 == d1) { acc[r][q] = fmaf(d1, d1, acc[r][q]); cnt[r][q] += 1; }
+                                    if (d2 == d2) { acc[r][q] = fmaf(d2, d2, acc[r][q]); cnt[r][q] += 1; }
+                                    if (d3 == d3) { acc[r][q] = fmaf(d3, d3, acc[r][q]); cnt[r][q] += 1; }
+                                }
+                        }
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
                         if (++stage == S) { stage = 0; phase ^= 1; }
@@ -208,7 +236,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
 #pragma unroll
                 for (int q = 0; q < QC; ++q) {
                     float a = acc[r][q];
-                    int n = cnt[r][q];
+                    int n = clean ? cnt[r][0] : cnt[r][q];
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) {
                         a += __shfl_xor_sync(0xffffffffu, a, off);
@@ -285,8 +313,9 @@ int pixel_grid(const sky_bank* b, int64_t n_rows) {
     return static_cast<int>(g < 1 ? 1 : g);
 }
 
-int launch_pixel_fold(const float* q, const unsigned char* mask, int64_t n, float* qp, cudaStream_t st) {
-    pixel_fold_query_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(q, mask, n, qp);
+int launch_pixel_fold(const float* q, const unsigned char* mask, int64_t n, int D, float* qp, int* excl, cudaStream_t st) {
+    SKY_CUDA(cudaMemsetAsync(excl, 0, static_cast<size_t>((n + D - 1) / D) * sizeof(int), st));
+    pixel_fold_query_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(q, mask, n, D, qp, excl);
     SKY_LAUNCH_CHECK("pixel_fold_query_kernel");
     return SKY_OK;
 }
@@ -300,8 +329,8 @@ static int pixel_launch_one(const PixelParams& p, int grid, size_t smem, cudaStr
 }
 
 // qp: folded queries [Q][D]; rows [row_lo, row_hi) of the bank; emit != null -> scores only
-int launch_pixel_search(const sky_bank* b, const float* qp, int Q, int64_t row_lo, int64_t row_hi, const SearchState& s,
-                        int grid, int qc, float* emit, cudaStream_t st) {
+int launch_pixel_search(const sky_bank* b, const float* qp, const int* excl, int Q, int64_t row_lo, int64_t row_hi,
+                        const SearchState& s, int grid, int qc, float* emit, cudaStream_t st) {
     int stages = kPxMaxStages;
     { const int e = env_knob("SKY_PX_STAGES", 0); if (e >= 2 && e < stages) stages = e; }
     const size_t smem = static_cast<size_t>(stages) * kPxChunk + px_fixed_bytes(qc);
@@ -309,6 +338,7 @@ int launch_pixel_search(const sky_bank* b, const float* qp, int Q, int64_t row_l
         PixelParams p;
         p.bank = reinterpret_cast<const unsigned char*>(b->data);
         p.qp = qp;
+        p.excl = excl;
         p.row_lo = row_lo; p.row_hi = row_hi;
         p.D = b->D; p.nch = (b->D + kPxChunkElems - 1) / kPxChunkElems;
         p.q0 = q0; p.nq = (Q - q0 < qc) ? (Q - q0) : qc;

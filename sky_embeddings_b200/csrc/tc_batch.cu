@@ -146,8 +146,17 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The warp stays converged (every lane polls the barriers and carries the warp-uniform descriptors), one elected
+        // lane issues; the descriptors are loop-carried and only incremented (stage = 48 KB = 3072 in the descriptor's
+        // address >> 4 field, k-step = 32 B = 2).  Inside an `if (lane == 0)` region ptxas wraps every UTCHMMA in an
+        // ELECT / R2UR loop and rebuilds both descriptors with ~50 dependent uniform-datapath instructions: ~120 cycles
+        // per MMA on the issuing thread, about as long as the 128 cycles a 128 x 256 x 16 MMA executes -- the tensor
+        // pipe then idles ~10 % of the time waiting for its next instruction.
+        {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileRows, kTbBN);
+            const uint32_t issuer = ptx::elect_one();
+            const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sStage));
+            uint64_t a_desc = a_desc0;
             int stage = 0;
             uint32_t phase = 0;
             for (int v = 0; v < visits; ++v) {
@@ -159,18 +168,19 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(sStage + static_cast<size_t>(stage) * kTbStage);
-                    const uint32_t b_addr = a_addr + kTbStageA;
+                    const uint64_t b_desc = a_desc + (kTbStageA >> 4);
+                    const uint32_t acc0 = kb != 0 ? 1u : 0u;
+                    if (issuer) {
+                        if (!(SKY_DBG(p) & 2)) {
 #pragma unroll
-                    for (int k = 0; k < kKBlock / 16; ++k) {
-                        const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_addr + k * 32);
-                        const uint64_t b_desc = ptx::make_sw128_kmajor_desc(b_addr + k * 32);
-                        if (!(SKY_DBG(p) & 2)) ptx::umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < kKBlock / 16; ++k) ptx::umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k ? 1u : acc0);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (kb == KB - 1) ptx::umma_commit(&tmem_full[acc]);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
-                    if (++stage == kTbStages) { stage = 0; phase ^= 1; }
+                    a_desc += kTbStage >> 4;
+                    if (++stage == kTbStages) { stage = 0; phase ^= 1; a_desc = a_desc0; }
                 }
-                ptx::umma_commit(&tmem_full[acc]);
             }
         }
     } else {

@@ -391,9 +391,9 @@ constexpr int kT2MaxStages = 8;                  // TMEM: 256 accumulator column
 // done; the odd CTA writes rows 9.. the same way), SKY_TW_DEBUG bit 5
 #ifdef SKY_EXPERIMENTS
 constexpr int kTwTraceLen = 1024;
-constexpr int kTwTraceRows = 9;
+constexpr int kTwTraceRows = 13;   // + 9..11 squarer warps 1..3 arrived, 12 MMA starts waiting for sq_bar
 __device__ unsigned long long g_tw_trace[2 * kTwTraceRows * kTwTraceLen];
-#define TW_TRACE(row, i) do { if ((SKY_DBG(p) & 32) && blockIdx.x < 2 && (i) < kTwTraceLen) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_tw_trace[(blockIdx.x * kTwTraceRows + (row)) * kTwTraceLen + (i)] = t_; } } while (0)
+#define TW_TRACE(row, i) do { if ((SKY_DBG(p) & 32) && blockIdx.x < 2 && (i) < kTwTraceLen && (threadIdx.x & 31) == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_tw_trace[(blockIdx.x * kTwTraceRows + (row)) * kTwTraceLen + (i)] = t_; } } while (0)
 #else
 #define TW_TRACE(row, i) do { } while (0)
 #endif
@@ -436,6 +436,7 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
     uint32_t* sHist = sLmax + kTwBN;                                                // [4][256]
     uint32_t* sTmemBase = sHist + 4 * 256;
     volatile int* sTilesDone = reinterpret_cast<volatile int*>(sTmemBase + 1);
+    volatile int* sBoot = sTilesDone + 1;   // 0 = not started, 1 = tile-0 maxima ready, 2 = bounds applied
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr bool largest = COS;
@@ -458,6 +459,7 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 8); }
         ptx::fence_barrier_init();
         *sTilesDone = 0;
+        *sBoot = 0;
     }
     if (warp == kT2MmaWarp) {
         ptx::tmem_alloc2(sTmemBase, 512);           // 2 x (D1 | D2) accumulators + S squared k-blocks, in both CTAs
@@ -544,39 +546,46 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
             if (lane == 0) {
                 if (rank == 0) ptx::mbar_arrive(&sq_bar[stage]);
                 else ptx::mbar_arrive_cluster(&sq_bar[stage], 0);
-                if (quarter == 0) TW_TRACE(2, i);
+                if (quarter == 0) TW_TRACE(2, i); else TW_TRACE(8 + quarter, i);
             }
             if (++stage == S) { stage = 0; phase ^= 1; }
         }
     } else if (warp == kT2MmaWarp) {
         // ===================== MMA issuer: the even CTA's warp drives both SMs =====================
-        // The warp stays converged (lane 0 polls, everyone computes the descriptors); one elected lane issues.
+        // The warp stays converged: every lane polls the barriers and carries the (warp-uniform) descriptors, one
+        // elected lane issues.  The descriptors are loop-carried and only ever incremented (a stage is 16 KB = 1024 in
+        // the descriptor's address >> 4 field, a resident k-block 4 KB = 256, a k-step 32 B = 2): rebuilding them from
+        // addresses every k-block costs ~50 dependent uniform-datapath instructions, several hundred cycles per
+        // stage on the one thread everything else waits for.
         if (rank == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * kTileRows, kTwBN);
             const uint32_t issuer = ptx::elect_one();
+            const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA));
+            const uint64_t ba_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sBa));
+            const uint64_t bw_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sBw));
+            const uint32_t sq0 = tmem_base + kTwSqBase;
             int stage = 0;
             uint32_t phase = 0;
+            uint64_t a_desc = a_desc0;
+            uint32_t a2_tmem = sq0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                if (lane == 0) { t2_wait_remote(&tmem_empty[acc], acc_phase ^ 1, pp.spin); TW_TRACE(5, it); }
-                __syncwarp();
+                t2_wait_remote(&tmem_empty[acc], acc_phase ^ 1, pp.spin);
+                TW_TRACE(5, it);
                 ptx::tc_fence_after();
                 const uint32_t d1 = tmem_base + static_cast<uint32_t>(acc * 2 * kTwBN);
                 const uint32_t d2 = d1 + kTwBN;
+                uint64_t ba_desc = ba_desc0, bw_desc = bw_desc0;
                 for (int kb = 0; kb < KB; ++kb) {
                     // 8 arrivals: each squarer warp of either CTA saw its own stage land (and, first time, its resident
                     // operands) and finished writing the squared copy
-                    if (lane == 0) { t2_wait_remote(&sq_bar[stage], phase, pp.spin); TW_TRACE(3, it * KB + kb); }
-                    __syncwarp();
+                    TW_TRACE(12, it * KB + kb);
+                    t2_wait_remote(&sq_bar[stage], phase, pp.spin);
+                    TW_TRACE(3, it * KB + kb);
                     ptx::tc_fence_after();
-                    const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + static_cast<size_t>(stage) * kTwStageA));
-                    const uint64_t ba_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sBa + static_cast<size_t>(kb) * kT2BBlock));
-                    const uint64_t bw_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sBw + static_cast<size_t>(kb) * kT2BBlock));
-                    const uint32_t a2_tmem = tmem_base + kTwSqBase + stage * kTwSqCols;
                     const uint32_t acc0 = kb != 0 ? 1u : 0u;
                     if (issuer) {
-                        // a k-step of 16 elements = 32 bytes = 2 in the descriptor's (address >> 4) field
                         if (!(SKY_DBG(p) & 8)) {
 #pragma unroll
                             for (int k = 0; k < kKBlock / 16; ++k) ptx::umma2_bf16(d1, a_desc + 2 * k, ba_desc + 2 * k, idesc, k ? 1u : acc0);
@@ -589,8 +598,11 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
                         if (kb == KB - 1) ptx::umma2_commit_mc(&tmem_full[acc], 0b11);   // both epilogues may read
                         TW_TRACE(4, it * KB + kb);
                     }
-                    __syncwarp();
-                    if (++stage == S) { stage = 0; phase ^= 1; }
+                    ba_desc += kT2BBlock >> 4;
+                    bw_desc += kT2BBlock >> 4;
+                    a_desc += kTwStageA >> 4;
+                    a2_tmem += kTwSqCols;
+                    if (++stage == S) { stage = 0; phase ^= 1; a_desc = a_desc0; a2_tmem = sq0; }
                 }
             }
         }
@@ -608,6 +620,37 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
             __syncwarp();
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 2 * kTwBN);
+            if (it == 0 && p.use_gtau && !(SKY_DBG(p) & 4)) {
+                // BOOTSTRAP (once per launch, as K2): with no bound yet every row of the first tile would be a candidate
+                // for every query (8192 inserts per CTA, and lists that the merge then has to wade through).  Read the
+                // accumulators twice: this first pass only takes the per-query maximum of the tile, the exchange warp
+                // trades maxima with the other CTAs, and the normal pass below runs with a grid-wide bound in place.
+#pragma unroll 1
+                for (int c = 0; c < kTwBN / 32; ++c) {
+                    uint32_t v1[32], v2[32];
+                    ptx::tmem_ld_32x32b_x32(taddr + c * 32, v1);
+                    ptx::tmem_ld_32x32b_x32(taddr + kTwBN + c * 32, v2);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int q = c * 32 + j;
+                        const float d1 = __uint_as_float(v1[j]), d2 = __uint_as_float(v2[j]);
+                        const float sv = COS ? __fdividef(d1, fmaf(sQ1[q], sqrtf(fmaxf(d2, 0.f)), 1e-6f)) : (sQ1[q] - 2.0f * d1 + d2) * sQ2[q];
+                        const uint32_t key = (valid && q < p.nq) ? score_to_key(sv, largest) : 0u;
+                        const uint32_t best = __reduce_max_sync(0xffffffffu, key);
+                        if (lane == 0 && best) reds_max_u32(sink.lmax + q * 4, best);
+                    }
+                }
+                ptx::named_bar_sync(1, 128);
+                if (e == 0 && lane == 0) *sBoot = 1;
+                if (lane == 0) {
+                    const long long t_end = clock64() + 60000;         // ~30 us: never wait for a bound forever
+                    while (*sBoot != 2 && clock64() < t_end) __nanosleep(100);
+                }
+                __syncwarp();
+                if (e * 32 + lane < kTwBN) tw_prefilter_coeffs<COS>(e * 32 + lane, p.nq, sink, sQ1, sQ2, sC);
+                ptx::named_bar_sync(1, 128);
+            }
             tw_score_tile<COS>(taddr, static_cast<uint32_t>(row), valid, p.nq, SKY_DBG(p), sink, sQ1, sQ2, sC, [&]() {
                 if (lane == 0) {
                     if (rank == 0) ptx::mbar_arrive(&tmem_empty[acc]);
@@ -635,6 +678,27 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
             int round = 0;
             uint32_t last_pub[kTwBN / 32] = {};
             uint32_t last_lo = 0;
+            // bootstrap: wait for the tile-0 maxima, then trade them until every query has a bound
+            while (*sBoot == 0 && *sTilesDone < my_tiles) __nanosleep(50);
+            {
+                const long long t_end = clock64() + 40000;
+                bool all = false;
+                while (!all && clock64() < t_end) {
+                    exchange_publish_changed(sink, p.nq, my_row, last_pub);
+                    const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot, p.k);
+                    if (lane == 0 && lo > last_lo) atomicMax(p.gtau + p.q0 + rq, lo);
+                    last_lo = lo > last_lo ? lo : last_lo;
+                    bool mine_ok = true;
+                    for (int q = lane; q < p.nq; q += 32) {
+                        const uint32_t g = ld_cg_u32(p.gtau + p.q0 + q);
+                        exchange_apply(sink, q, g);
+                        mine_ok = mine_ok && (g != 0u);
+                    }
+                    all = __all_sync(0xffffffffu, mine_ok);
+                }
+                __syncwarp();
+                if (lane == 0) *sBoot = 2;
+            }
             while (*sTilesDone < my_tiles) {
                 exchange_publish_changed(sink, p.nq, my_row, last_pub);
                 const uint32_t lo = exchange_reduce(p.gtop + p.q0 + rq, p.p_stride, p.Qtot, p.k);
@@ -713,7 +777,7 @@ size_t tc_weighted_scratch_bytes(const sky_bank* b) {
 }
 
 static size_t tw2_tail_bytes() {
-    return (3 * kT2MaxStages + 1 + 4) * sizeof(uint64_t) + 16 + kTwBN * (8 + 6 * 4) + 4 * 256 * 4 + 16;
+    return (3 * kT2MaxStages + 1 + 4) * sizeof(uint64_t) + 16 + kTwBN * (8 + 6 * 4) + 4 * 256 * 4 + 32;
 }
 
 // ring depth of the CTA-pair kernel (0 = the resident query halves do not leave room for a useful ring)

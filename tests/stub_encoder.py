@@ -28,6 +28,9 @@ class StubViT(torch.nn.Module):
 
     def forward_features(self, samples, ra_dec=None, mask=None, reshape_out=False):
         B, C, H, W = samples.shape
+        # missing bands / pixels are NaN; the reference's encoder replaces them with its (zero-initialised) mask values
+        # before patch embedding (utils/mim_vit.py:388-392)
+        samples = torch.where(torch.isnan(samples), torch.zeros_like(samples), samples)
         p = self.patch
         x = samples.reshape(B, C, H // p, p, W // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B, self.n_patch, C * p * p)
         x = x @ self.proj
