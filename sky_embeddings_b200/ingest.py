@@ -32,9 +32,11 @@ def open_h5(path):
     """``h5py.File`` when h5py is importable, else the pure-Python reader (contiguous datasets only)."""
     try:
         import h5py  # noqa: PLC0415
-        return h5py.File(path, "r")
     except ImportError:
-        return h5lite.H5File(path)
+        h5py = None
+    if h5py is not None and hasattr(h5py, "File"):
+        return h5py.File(path, "r")
+    return h5lite.H5File(path)
 
 
 def _stream(device):
@@ -144,11 +146,11 @@ class H5Cutouts:
     def _stage(self, rows, device):
         """Rows of the file -> CUDA f32 [n, C, H, W]: one gathered host copy into pinned memory, one async H2D."""
         if isinstance(rows, slice):
-            host = np.ascontiguousarray(self.cutouts[rows], dtype=np.float32)
+            host = np.array(self.cutouts[rows], dtype=np.float32)          # a copy: the map is read-only
         else:
             rows = np.asarray(rows)
-            host = np.ascontiguousarray(self.cutouts[rows] if len(rows) else
-                                        np.zeros((0,) + tuple(self.cutouts.shape[1:]), np.float32), dtype=np.float32)
+            host = np.array(self.cutouts[rows] if len(rows) else
+                            np.zeros((0,) + tuple(self.cutouts.shape[1:]), np.float32), dtype=np.float32)
         t = torch.from_numpy(host)
         if device.type == "cuda" and t.numel():
             t = t.pin_memory()
