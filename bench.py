@@ -379,7 +379,10 @@ def run_search_workload(name, wl, args, dev, steps, warmup, strong, headline):
     def step_device():
         if world == 1:
             return local_search(t_dev, w_dev)
-        # local top-k straight into the exchange buffer, then the candidate exchange + merge
+        if args.exchange == "peer":
+            # shard search whose merge kernel writes into every peer, then the flag-waiting merge (sky_search_sharded)
+            return xchg.search(bank, t_dev, w_dev, metric=metric, path=args.path, idx_offset=row_lo)
+        # local top-k straight into the exchange buffer, then one NCCL all-gather + merge
         local_search(t_dev, w_dev, xchg.scores, xchg.idx)
         return xchg.merge(metric)
 
@@ -390,8 +393,11 @@ def run_search_workload(name, wl, args, dev, steps, warmup, strong, headline):
                                     out_scores=out_s_host, out_idx=out_i_host)
         td = t_host.to(dev, non_blocking=True)
         wd = w_host.to(dev, non_blocking=True) if w_host is not None else None
-        local_search(td, wd, xchg.scores, xchg.idx)
-        s, i = xchg.merge(metric)
+        if args.exchange == "peer":
+            s, i = xchg.search(bank, td, wd, metric=metric, path=args.path, idx_offset=row_lo)
+        else:
+            local_search(td, wd, xchg.scores, xchg.idx)
+            s, i = xchg.merge(metric)
         out_s_host.copy_(s, non_blocking=True)
         out_i_host.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -200,6 +200,12 @@ SKY_API int sky_exchange_destroy(sky_exchange_t* x);
  * out_scores / out_idx [Q, k_out]: the global top-k_out, identical on every rank. */
 SKY_API int sky_exchange_merge(sky_exchange_t* x, const float* scores, const int64_t* idx, int Q, int k, int k_out,
                        int metric, float* out_scores, int64_t* out_idx, void* stream);
+/* sky_search over this rank's shard + the exchange in one call: the shard merge kernel writes its [Q, k] result
+ * straight into every peer (no separate push), then the flag-waiting merge yields the GLOBAL top-k on every rank.
+ * idx_offset = first global row of the shard.  Collective: every rank calls it with the same Q and k. */
+SKY_API int sky_search_sharded(sky_bank_t* bank, sky_exchange_t* x, const float* t, const float* w, int Q, int metric,
+                       int combine, int n_top_sims, int k, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                       int path, void* stream);
 
 /* Timing of the dominant (scoring) kernel of each search with CUDA events recorded on the launch
  * stream right around it: enable, run searches, then read (#launches, total ms); read synchronises. */

@@ -58,6 +58,7 @@ SIGNATURES = {
     "sky_exchange_local_ptr": (_vp, [_vp]),
     "sky_exchange_destroy": (_i, [_vp]),
     "sky_exchange_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sky_search_sharded": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _i, _vp]),
     "sky_profile_enable": (_i, [_vp, _i]),
     "sky_profile_read": (_i, [_vp, C.POINTER(_i64), C.POINTER(C.c_double), _i]),
     "sky_launch_count": (_i64, [_i]),

@@ -357,7 +357,8 @@ int sky_query_from_targets(const sky_bank_t* b, const float* targets, int64_t T_
 }
 
 static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int metric, int combine, int n_top_sims,
-                       int k, int64_t idx_offset, float* out_scores, int64_t* out_idx, int path, cudaStream_t st) {
+                       int k, int64_t idx_offset, float* out_scores, int64_t* out_idx, int path, cudaStream_t st,
+                       XchgTarget* xt = nullptr) {
     if (!b || !t || !out_scores || !out_idx) return set_error(SKY_ERR_ARG, "NULL argument");
     if (!valid_metric(metric)) return set_error(SKY_ERR_ARG, "unknown metric %d (the reference accepts cosine, MSE, MAE)", metric);
     if (!valid_combine(combine)) return set_error(SKY_ERR_ARG, "unknown combine %d", combine);
@@ -382,7 +383,7 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
         if (rcw) return rcw;
         rcw = launch_tc_weighted(b, t, w, Q, metric, sw, st);      // its packing kernel zeroes the exchange state
         if (rcw) return rcw;
-        return launch_merge_lists(sw, metric, idx_offset, out_scores, out_idx, st);
+        return launch_merge_lists(sw, metric, idx_offset, out_scores, out_idx, st, xt);
     }
     // small query batches stay on the streaming SIMT kernel (HBM bound there); larger ones need MMA
     const bool use_tc = tc_ok && (path == SKY_PATH_TENSOR || (path == SKY_PATH_AUTO && Q > kAutoStreamMaxQ));
@@ -445,7 +446,7 @@ static int search_impl(sky_bank_t* b, const float* t, const float* w, int Q, int
             if (rc) return rc;
         }
     }
-    return launch_merge_lists(s, metric, idx_offset, out_scores, out_idx, st);
+    return launch_merge_lists(s, metric, idx_offset, out_scores, out_idx, st, xt);
 }
 
 int sky_search(sky_bank_t* b, const float* t, const float* w, int Q, int metric, int combine, int n_top_sims, int k,
@@ -454,6 +455,29 @@ int sky_search(sky_bank_t* b, const float* t, const float* w, int Q, int metric,
     DeviceGuard g(b->device);
     return search_impl(b, t, w, Q, metric, combine, n_top_sims, k, idx_offset, out_scores, out_idx, path,
                        static_cast<cudaStream_t>(stream));
+}
+
+int sky_search_sharded(sky_bank_t* b, sky_exchange_t* x, const float* t, const float* w, int Q, int metric, int combine,
+                       int n_top_sims, int k, int64_t idx_offset, float* out_scores, int64_t* out_idx, int path, void* stream) {
+    if (!b || !x) return set_error(SKY_ERR_ARG, "bank / exchange is NULL");
+    if (xchg_device(x) != b->device) return set_error(SKY_ERR_ARG, "the exchange lives on device %d, the bank on %d", xchg_device(x), b->device);
+    DeviceGuard g(b->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    XchgTarget xt;
+    int rc = xchg_begin(x, Q, k, &xt);
+    if (rc) return rc;
+    // the shard's result is delivered into this rank's slot of every peer: by the shard merge kernel itself where the
+    // path ends in one (fused), else it lands in the local slot first and one push kernel forwards it
+    float* ls = nullptr;
+    int64_t* li = nullptr;
+    xchg_local_slot(xt, Q, k, &ls, &li);
+    rc = search_impl(b, t, w, Q, metric, combine, n_top_sims, k, idx_offset, ls, li, path, st, &xt);
+    if (rc) return rc;
+    if (!xt.fused) {
+        rc = launch_xchg_push(xt, ls, li, Q, k, /*skip_self=*/1, b->device, st);
+        if (rc) return rc;
+    }
+    return launch_xchg_merge(xt, Q, k, k, metric, out_scores, out_idx, b->device, st);
 }
 
 int sky_search_host(sky_bank_t* b, const float* h_t, const float* h_w, int Q, int metric, int combine, int n_top_sims,
@@ -480,7 +504,26 @@ int sky_search_host(sky_bank_t* b, const float* h_t, const float* h_w, int Q, in
         void* m_s = mapped(h_out_scores);
         void* m_i = mapped(h_out_idx);
         if (m_t && (m_w || !h_w) && m_s && m_i) {
-            int rc0 = search_impl(b, static_cast<const float*>(m_t), static_cast<const float*>(m_w), Q, metric, combine, n_top_sims, k,
+            // the tensor paths read the queries once (packing kernel); the streaming kernels read them in every CTA,
+            // which is slow over PCIe (measured +0.11 ms on a Q = 1 search): those get one staged copy of the queries
+            const bool packed_once = b->dtype == SKY_BF16 && b->L == 1 && metric != SKY_MAE && n_top_sims == 0 &&
+                                     (path == SKY_PATH_TENSOR || path == SKY_PATH_BATCH || (path == SKY_PATH_AUTO && Q > kAutoStreamMaxQ));
+            const float* q_t = static_cast<const float*>(m_t);
+            const float* q_w = static_cast<const float*>(m_w);
+            if (!packed_once) {
+                size_t scratch0 = tc_scratch_bytes(b, Q);
+                if (tc_weighted_scratch_bytes(b) > scratch0) scratch0 = tc_weighted_scratch_bytes(b);
+                const size_t o0 = static_cast<size_t>(round_up(static_cast<int64_t>(scratch0), 256));
+                int rcs = ensure_ws2(b, o0 + 2 * round_up(qb, 256));
+                if (rcs) return rcs;
+                float* d_t0 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(b->ws2) + o0);
+                float* d_w0 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(b->ws2) + o0 + round_up(qb, 256));
+                SKY_CUDA(cudaMemcpyAsync(d_t0, h_t, qb, cudaMemcpyHostToDevice, st));
+                if (h_w) SKY_CUDA(cudaMemcpyAsync(d_w0, h_w, qb, cudaMemcpyHostToDevice, st));
+                q_t = d_t0;
+                q_w = h_w ? d_w0 : nullptr;
+            }
+            int rc0 = search_impl(b, q_t, q_w, Q, metric, combine, n_top_sims, k,
                                   idx_offset, static_cast<float*>(m_s), static_cast<int64_t*>(m_i), path, st);
             if (rc0) return rc0;
             SKY_CUDA(cudaStreamSynchronize(st));

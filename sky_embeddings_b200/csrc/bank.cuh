@@ -6,6 +6,8 @@
 
 #include "common.cuh"
 
+struct sky_exchange;      // exchange.cu
+
 struct sky_bank {
     int device = 0;
     int num_sms = 0;
@@ -128,10 +130,27 @@ bool tc_batch_supported(const sky_bank* b, int metric, bool weighted, int n_top,
 int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64_t idx_offset, float* out_scores,
                     int64_t* out_idx, cudaStream_t st);
 
+// exchange.cu: where a sharded search delivers its [Q, k] result (every peer's slot of this rank + a flag per query)
+constexpr int kMaxPeers = 16;
+struct XchgTarget {
+    unsigned char* base[kMaxPeers];   // mapped base of every rank's exchange buffer (base[rank] = local)
+    int world = 0, rank = 0;
+    size_t slot_units = 0;            // int64 units of one rank's block
+    int max_Q = 0, parity = 0;
+    unsigned seq = 0;
+    bool fused = false;               // set by the launcher that delivered the result itself
+};
+
+int xchg_begin(sky_exchange* x, int Q, int k, XchgTarget* xt);
+void xchg_local_slot(const XchgTarget& xt, int Q, int k, float** scores, int64_t** idx);
+int launch_xchg_push(const XchgTarget& xt, const float* scores, const int64_t* idx, int Q, int k, int skip_self, int device, cudaStream_t st);
+int launch_xchg_merge(const XchgTarget& xt, int Q, int k, int k_out, int metric, float* out_scores, int64_t* out_idx, int device, cudaStream_t st);
+int xchg_device(const sky_exchange* x);
+
 // merge.cu
 int launch_init_state(const SearchState& s, int p_active, cudaStream_t st);
 int launch_merge_lists(const SearchState& s, int metric, int64_t idx_offset, float* out_scores, int64_t* out_idx,
-                       cudaStream_t st);
+                       cudaStream_t st, XchgTarget* xt = nullptr);
 int launch_merge_candidates(const float* scores, const int64_t* idx, int R, int Q, int k_in, int64_t stride_s,
                             int64_t stride_i, int k_out, int metric, float* out_scores, int64_t* out_idx, cudaStream_t st);
 

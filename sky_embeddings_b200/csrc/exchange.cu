@@ -33,35 +33,27 @@ struct sky_exchange {
 
 namespace sky {
 
-constexpr int kMaxPeers = 16;
 constexpr int kXchgThreads = 256;
 
 struct PeerPtrs { unsigned char* base[kMaxPeers]; };
 
-__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
+struct DeviceGuardX {
+    int prev = -1;
+    explicit DeviceGuardX(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuardX() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
-// byte offsets inside a rank's buffer
-__host__ __device__ __forceinline__ size_t slot_off(size_t slot_units, int world, int parity, int r) {
-    return (static_cast<size_t>(parity) * world + r) * slot_units * 8;
-}
-__host__ __device__ __forceinline__ size_t flag_off(size_t slot_units, int world, int max_Q, int parity, int r) {
-    return 2 * static_cast<size_t>(world) * slot_units * 8 + (static_cast<size_t>(parity) * world + r) * static_cast<size_t>(max_Q) * 4;
-}
+#define slot_off xchg_slot_off
+#define flag_off xchg_flag_off
 
 // grid = queries; CTA q copies row q of the local (scores, idx) into every peer, then raises that query's flag there
 __global__ void __launch_bounds__(kXchgThreads)
 xchg_push_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, int Q, int k, PeerPtrs peers, int world,
-                 int rank, size_t slot_units, int max_Q, int parity, unsigned seq) {
+                 int rank, size_t slot_units, int max_Q, int parity, unsigned seq, int skip_self) {
     const int q = blockIdx.x;
     const size_t n = static_cast<size_t>(Q) * k;
     for (int p = 0; p < world; ++p) {
+        if (skip_self && p == rank) continue;           // the source IS this rank's own slot
         unsigned char* slot = peers.base[p] + slot_off(slot_units, world, parity, rank);
         int64_t* di = reinterpret_cast<int64_t*>(slot) + static_cast<size_t>(q) * k;
         float* ds = reinterpret_cast<float*>(slot + n * 8) + static_cast<size_t>(q) * k;
@@ -137,6 +129,51 @@ static int next_pow2_x(int v) {
     while (p < v) p <<= 1;
     return p;
 }
+
+
+// Start one exchange: next sequence number / slot parity, and where every peer keeps this rank's block.
+int xchg_begin(sky_exchange* x, int Q, int k, XchgTarget* xt) {
+    if (!x) return set_error(SKY_ERR_ARG, "exchange is NULL");
+    if (!x->ready) return set_error(SKY_ERR_STATE, "exchange is not connected: call sky_exchange_open first");
+    if (Q < 1 || Q > x->max_Q || k < 1 || k > x->max_k)
+        return set_error(SKY_ERR_ARG, "Q=%d k=%d exceed the exchange capacity (%d, %d)", Q, k, x->max_Q, x->max_k);
+    const unsigned seq = ++x->seq;
+    for (int r = 0; r < kMaxPeers; ++r) xt->base[r] = r < x->world ? x->peer[r] : nullptr;
+    xt->world = x->world; xt->rank = x->rank; xt->slot_units = x->slot_units; xt->max_Q = x->max_Q;
+    xt->parity = static_cast<int>(seq & 1u); xt->seq = seq; xt->fused = false;
+    return SKY_OK;
+}
+
+// this rank's own slot of the current exchange (a search can deliver its result there and push it afterwards)
+void xchg_local_slot(const XchgTarget& xt, int Q, int k, float** scores, int64_t** idx) {
+    unsigned char* slot = xt.base[xt.rank] + xchg_slot_off(xt.slot_units, xt.world, xt.parity, xt.rank);
+    *idx = reinterpret_cast<int64_t*>(slot);
+    *scores = reinterpret_cast<float*>(slot + static_cast<size_t>(Q) * k * 8);
+}
+
+int launch_xchg_push(const XchgTarget& xt, const float* scores, const int64_t* idx, int Q, int k, int skip_self, int device, cudaStream_t st) {
+    DeviceGuardX g(device);
+    PeerPtrs pp;
+    for (int r = 0; r < kMaxPeers; ++r) pp.base[r] = xt.base[r];
+    xchg_push_kernel<<<Q, kXchgThreads, 0, st>>>(scores, idx, Q, k, pp, xt.world, xt.rank, xt.slot_units, xt.max_Q, xt.parity, xt.seq, skip_self);
+    SKY_LAUNCH_CHECK("xchg_push_kernel");
+    return SKY_OK;
+}
+
+int launch_xchg_merge(const XchgTarget& xt, int Q, int k, int k_out, int metric, float* out_scores, int64_t* out_idx, int device, cudaStream_t st) {
+    if (k_out < 1 || k_out > 4096) return set_error(SKY_ERR_ARG, "k_out=%d out of range", k_out);
+    DeviceGuardX g(device);
+    const int kpad = next_pow2_x(k_out);
+    const int n = xt.world * k;
+    const size_t smem = static_cast<size_t>(kpad + (n <= kRankSortMax ? n : 0)) * sizeof(uint64_t);
+    SKY_CUDA(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    xchg_merge_kernel<<<Q, kXchgThreads, smem, st>>>(xt.base[xt.rank], xt.world, xt.slot_units, xt.max_Q, xt.parity, xt.seq, Q, k, k_out, kpad,
+                                                    metric_largest(metric) ? 1 : 0, out_scores, out_idx);
+    SKY_LAUNCH_CHECK("xchg_merge_kernel");
+    return SKY_OK;
+}
+
+int xchg_device(const sky_exchange* x) { return x->device; }
 
 }  // namespace sky
 
@@ -248,33 +285,14 @@ int sky_exchange_destroy(sky_exchange_t* x) {
 int sky_exchange_merge(sky_exchange_t* x, const float* scores, const int64_t* idx, int Q, int k, int k_out, int metric,
                        float* out_scores, int64_t* out_idx, void* stream) {
     if (!x || !scores || !idx || !out_scores || !out_idx) return set_error(SKY_ERR_ARG, "NULL argument");
-    if (!x->ready) return set_error(SKY_ERR_STATE, "exchange is not connected: call sky_exchange_open first");
-    if (Q < 1 || Q > x->max_Q || k < 1 || k > x->max_k || k_out < 1 || k_out > 4096)
-        return set_error(SKY_ERR_ARG, "Q=%d k=%d exceed the exchange capacity (%d, %d)", Q, k, x->max_Q, x->max_k);
     if (metric != SKY_COSINE && metric != SKY_MSE && metric != SKY_MAE) return set_error(SKY_ERR_ARG, "unknown metric %d", metric);
-    int prev = -1;
-    cudaGetDevice(&prev);
-    if (cudaSetDevice(x->device) != cudaSuccess) return set_error(SKY_ERR_CUDA, "cudaSetDevice(%d) failed", x->device);
+    XchgTarget xt;
+    int rc = xchg_begin(x, Q, k, &xt);
+    if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned seq = ++x->seq;
-    const int parity = static_cast<int>(seq & 1u);
-    PeerPtrs pp;
-    for (int r = 0; r < kMaxPeers; ++r) pp.base[r] = r < x->world ? x->peer[r] : nullptr;
-    xchg_push_kernel<<<Q, kXchgThreads, 0, st>>>(scores, idx, Q, k, pp, x->world, x->rank, x->slot_units, x->max_Q, parity, seq);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) {
-        const int kpad = next_pow2_x(k_out);
-        const int n = x->world * k;
-        const size_t smem = static_cast<size_t>(kpad + (n <= kRankSortMax ? n : 0)) * sizeof(uint64_t);
-        cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        xchg_merge_kernel<<<Q, kXchgThreads, smem, st>>>(x->local, x->world, x->slot_units, x->max_Q, parity, seq, Q, k, k_out, kpad,
-                                                        metric_largest(metric) ? 1 : 0, out_scores, out_idx);
-        e = cudaGetLastError();
-    }
-    cudaSetDevice(prev);
-    count_launch(2);
-    if (e != cudaSuccess) return set_error(SKY_ERR_CUDA, "exchange kernels failed to launch: %s", cudaGetErrorString(e));
-    return SKY_OK;
+    rc = launch_xchg_push(xt, scores, idx, Q, k, /*skip_self=*/0, x->device, st);
+    if (rc) return rc;
+    return launch_xchg_merge(xt, Q, k, k_out, metric, out_scores, out_idx, x->device, st);
 }
 
 }  // extern "C"

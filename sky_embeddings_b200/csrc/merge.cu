@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kMergeThreads)
 merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ counts,
                    const uint32_t* __restrict__ gtop, int P, int p_stride, int Qtot, int cap, int k, int kpad,
                    int use_gtau, int largest, int64_t idx_offset, float* __restrict__ out_scores,
-                   int64_t* __restrict__ out_idx) {
+                   int64_t* __restrict__ out_idx, const XchgTarget xt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
     uint64_t* pool = sel + kpad;                              // [kPool]
@@ -152,6 +152,22 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
         block_select_sort(fetch, P * cap, k, kpad, sel, hist, scratch);
     }
     __syncthreads();
+    if (xt.world > 0) {
+        // sharded search: the shard's top-k of query q goes straight into this rank's slot of EVERY peer's exchange
+        // buffer (plain stores over NVLink), then one flag per peer says "query q of search `seq` has landed"
+        const size_t nq = static_cast<size_t>(Qtot) * k;
+        for (int p = 0; p < xt.world; ++p) {
+            unsigned char* slot = xt.base[p] + xchg_slot_off(xt.slot_units, xt.world, xt.parity, xt.rank);
+            int64_t* di = reinterpret_cast<int64_t*>(slot) + static_cast<size_t>(q) * k;
+            float* ds = reinterpret_cast<float*>(slot + nq * 8) + static_cast<size_t>(q) * k;
+            for (int j = tid; j < k; j += kMergeThreads) write_result(sel[j], largest != 0, idx_offset, ds + j, di + j);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < xt.world)
+            st_release_sys_u32(reinterpret_cast<unsigned*>(xt.base[tid] + xchg_flag_off(xt.slot_units, xt.world, xt.max_Q, xt.parity, xt.rank)) + q, xt.seq);
+        return;
+    }
     for (int j = tid; j < k; j += kMergeThreads)
         write_result(sel[j], largest != 0, idx_offset, out_scores + static_cast<size_t>(q) * k + j,
                      out_idx + static_cast<size_t>(q) * k + j);
@@ -220,15 +236,16 @@ int launch_init_state(const SearchState& s, int p_active, cudaStream_t st) {
 }
 
 int launch_merge_lists(const SearchState& s, int metric, int64_t idx_offset, float* out_scores, int64_t* out_idx,
-                       cudaStream_t st) {
+                       cudaStream_t st, XchgTarget* xt) {
     if (s.k > kMaxK) return set_error(SKY_ERR_UNSUPPORTED, "k=%d exceeds the merge limit %d", s.k, kMaxK);
     const int kpad = next_pow2(s.k);
     const size_t smem = static_cast<size_t>(kpad + kPool) * sizeof(uint64_t);
     SKY_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     merge_lists_kernel<<<s.Qtot, kMergeThreads, smem, st>>>(s.lists, s.counts, s.gtop, s.P, s.p_stride, s.Qtot, s.cap,
                                                            s.k, kpad, s.use_gtau, metric_largest(metric) ? 1 : 0,
-                                                           idx_offset, out_scores, out_idx);
+                                                           idx_offset, out_scores, out_idx, xt ? *xt : XchgTarget{});
     SKY_LAUNCH_CHECK("merge_lists_kernel");
+    if (xt) xt->fused = true;
     return SKY_OK;
 }
 

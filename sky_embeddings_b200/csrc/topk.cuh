@@ -279,6 +279,24 @@ __device__ __forceinline__ void exchange_apply(const Sink& s, int q, uint32_t lo
     if (lo != 0u) sink_raise(s, q, (static_cast<uint64_t>(lo) << 32) - 1ull);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-memory exchange layout (csrc/exchange.cu): a rank's buffer = slots[2][world][slot_units] int64 | flags[2][world][max_Q] u32
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ size_t xchg_slot_off(size_t slot_units, int world, int parity, int r) {
+    return (static_cast<size_t>(parity) * world + r) * slot_units * 8;
+}
+__host__ __device__ __forceinline__ size_t xchg_flag_off(size_t slot_units, int world, int max_Q, int parity, int r) {
+    return 2 * static_cast<size_t>(world) * slot_units * 8 + (static_cast<size_t>(parity) * world + r) * static_cast<size_t>(max_Q) * 4;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Zero the grid-wide exchange state of a search (gtop / gtau / counts) from inside another kernel's grid: the query
 // packing kernels of the tensor paths do this on the side, which saves the separate init_state launch.
 struct StateInit {

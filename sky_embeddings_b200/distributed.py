@@ -131,6 +131,15 @@ class PeerExchange:
             C.c_void_p(self.out_idx.data_ptr()), _stream(self.device)))
         return self.out_scores, self.out_idx
 
+    def search(self, bank, t, w=None, metric="cosine", combine="min", n_top_sims=None, path="auto", idx_offset=0):
+        """The fused route: `bank`'s shard search delivers its result straight into every peer (the shard merge kernel
+        writes over NVLink), then the flag-waiting merge -- sky_search_sharded.  Returns the global (scores, idx)."""
+        if self.world == 1:
+            return bank.search(t, w, self.k, metric, combine, n_top_sims, path, idx_offset=idx_offset,
+                               out_scores=self.out_scores, out_idx=self.out_idx)
+        return bank.search_sharded(self._h, t, w, self.k, metric, combine, n_top_sims, path, idx_offset=idx_offset,
+                                   out_scores=self.out_scores, out_idx=self.out_idx)
+
     def close(self):
         if getattr(self, "_h", None):
             from . import _lib as L
@@ -187,9 +196,12 @@ class ShardedBank:
                     self._xchg.close()
                 self._xchg = make_exchange(Q, k, self.bank.device, self.group, self.exchange)
             x = self._xchg
-            self.bank.search(t, w, k, metric, combine, n_top_sims, path, idx_offset=self.row_lo,
-                             out_scores=x.scores, out_idx=x.idx)
-            s, i = x.merge(metric)
+            if isinstance(x, PeerExchange):
+                s, i = x.search(self.bank, t, w, metric, combine, n_top_sims, path, idx_offset=self.row_lo)
+            else:
+                self.bank.search(t, w, k, metric, combine, n_top_sims, path, idx_offset=self.row_lo,
+                                 out_scores=x.scores, out_idx=x.idx)
+                s, i = x.merge(metric)
             return s.clone(), i.clone()
         return sharded_search(
             lambda: self.bank.search(t, w, k, metric, combine, n_top_sims, path, idx_offset=self.row_lo),

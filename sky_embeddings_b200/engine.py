@@ -239,6 +239,23 @@ class Bank:
                                     _ptr(scores), _ptr(idx), L.PATHS[path], _stream(self.device)))
         return scores, idx
 
+    def search_sharded(self, exchange_handle, t, w=None, k=100, metric="cosine", combine="min", n_top_sims=None,
+                       path="auto", idx_offset=0, out_scores=None, out_idx=None):
+        """search() over this rank's shard + the peer-memory candidate exchange in one call (sky_search_sharded): returns
+        the GLOBAL top-k, identical on every rank.  exchange_handle: a connected sky_exchange (distributed.PeerExchange)."""
+        if metric not in L.METRICS:
+            raise ValueError(f"unknown metric {metric!r}: expected 'cosine', 'MSE' or 'MAE'")
+        if combine not in L.COMBINES:
+            raise ValueError(f"unknown combine {combine!r}: expected 'mean', 'min' or 'max'")
+        t, w = self._qprep(t, w)
+        Q = t.shape[0]
+        scores = torch.empty((Q, k), device=self.device, dtype=torch.float32) if out_scores is None else out_scores
+        idx = torch.empty((Q, k), device=self.device, dtype=torch.int64) if out_idx is None else out_idx
+        L.check(self.lib.sky_search_sharded(self._h, exchange_handle, _ptr(t), _ptr(w) if w is not None else None, Q,
+                                            L.METRICS[metric], L.COMBINES[combine], int(n_top_sims or 0), int(k),
+                                            int(idx_offset), _ptr(scores), _ptr(idx), L.PATHS[path], _stream(self.device)))
+        return scores, idx
+
     def search_host(self, t_host, w_host=None, k=100, metric="cosine", combine="min", n_top_sims=None,
                     path="auto", idx_offset=0, out_scores=None, out_idx=None):
         """Same as search() with HOST tensors in and out; the H2D / D2H copies happen inside the call."""

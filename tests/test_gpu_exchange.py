@@ -77,3 +77,50 @@ def test_exchange_rejects_bad_use():
     rc = lib.sky_exchange_merge(h, s.data_ptr(), i.data_ptr(), 8, 8, 8, 0, s.data_ptr(), i.data_ptr(), None)
     assert rc == -3 and b"not connected" in lib.sky_last_error()             # SKY_ERR_STATE before open
     lib.sky_exchange_destroy(h)
+
+
+@pytest.mark.parametrize("metric,weighted,Q,k", [("cosine", False, 64, 100), ("MSE", True, 16, 10), ("cosine", True, 3, 20), ("MSE", False, 300, 50)])
+def test_fused_sharded_search_equals_unsharded(metric, weighted, Q, k):
+    """sky_search_sharded on two shards of one bank (two logical ranks on one GPU, two streams): the shard merge kernel
+    delivers into both exchange buffers, the flag-waiting merge returns the global top-k -- identical, bit for bit, to
+    the search over the unsharded bank; K1 / K2 / K2w2 deliver fused, K2b (Q = 300) through the push kernel."""
+    from sky_embeddings_b200 import Bank, synth
+    from sky_embeddings_b200 import _lib as L
+    dev = torch.device("cuda:0")
+    n, D = 6000, 256
+    lat = torch.from_numpy(synth.latents(n, 1, D, stream=901)).to(dev)
+    full = Bank.from_latents(lat, norm_rows=64, dtype="bf16")
+    mu, sigma = full.norm()
+    cut = 3328                                            # shard boundary (a multiple of the 128-row tile is not required)
+    shards = []
+    for lo, hi in ((0, cut), (cut, n)):
+        b = Bank(hi - lo, 1, D, "bf16", dev)
+        b.set_norm(mu, sigma)
+        b.upload(lat[lo:hi], 0)
+        b.finalize()
+        shards.append((b, lo))
+    g = torch.Generator(device="cpu").manual_seed(7)
+    z = full.download()[:, 0]
+    t = (z[torch.randint(0, n, (Q,), generator=g)] + 0.1 * torch.randn(Q, D, generator=g).to(dev)).contiguous()
+    w = None
+    if weighted:
+        w = (torch.rand(Q, D, generator=g) + 0.25).to(dev)
+        w = (w / w.sum(1, keepdim=True)).contiguous()
+    want_s, want_i = full.search(t, w, k=k, metric=metric)
+    lib, hs = _mk(2, Q, k, dev)
+    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    for it in range(3):
+        outs = []
+        torch.cuda.synchronize()
+        for r, (b, lo) in enumerate(shards):
+            with torch.cuda.stream(streams[r]):
+                outs.append(b.search_sharded(hs[r], t, w, k=k, metric=metric, idx_offset=lo))
+        torch.cuda.synchronize()
+        for r in range(2):
+            assert torch.equal(outs[r][1], want_i), f"iteration {it} rank {r}: indices differ from the unsharded search"
+            assert torch.equal(outs[r][0].view(torch.int32), want_s.view(torch.int32)), f"iteration {it} rank {r}: scores differ"
+    for h in hs:
+        lib.sky_exchange_destroy(h)
+    for b, _ in shards:
+        b.close()
+    full.close()
