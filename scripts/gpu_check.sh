@@ -1,8 +1,18 @@
 #!/bin/bash
-# One gpurun call: smoke, GPU parity tests, short bench.  Every step is bounded by `timeout`.
-set -u
+# round 2: targeted GPU tests after a change + a few bench lines
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== smoke" ; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 ; echo "smoke rc=$?" ; tail -5 gpurun_out/smoke.log
-echo "== pytest gpu" ; timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider --timeout 600 ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1 ; echo "pytest rc=$?" ; tail -40 gpurun_out/pytest_gpu.log
-echo "== bench" ; timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err ; echo "bench rc=$?" ; cat gpurun_out/bench.json ; tail -5 gpurun_out/bench.err
+timeout 1500 python -m pytest tests/test_gpu_cli.py tests/test_gpu_ingest.py tests/test_properties.py tests/test_gpu_exchange.py tests/test_gpu_c1_real.py -m gpu -q --timeout 900 -p no:cacheprovider > gpurun_out/pytest_check.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_check.log | cut -c1-200
+for wl in q1w c2; do
+timeout 300 python bench.py --workload $wl --also none --no-cpu > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; echo "bench $wl rc=$?"; tail -2 gpurun_out/bench_$wl.err
+python - $wl <<'PY'
+import json, sys
+wl = sys.argv[1]
+try:
+    r = json.loads(open(f'gpurun_out/bench_{wl}.json').read().strip().splitlines()[-1])
+    rf = r['roofline']
+    print(f"{wl} value={r['value']:.1f} ms={r['ms_per_step']:.4f} e2e_ms={r['e2e']['ms_per_step']:.4f} kern_ms={rf['kernel_ms']:.4f} frac={rf['frac']:.3f} step_frac={rf.get('step_frac')} launches/step={r['gpu_launches_per_step']}")
+except Exception as e:
+    print('summary failed', e)
+PY
+done
