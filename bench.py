@@ -48,6 +48,7 @@ WORKLOADS = {
     # the reference's own regime: one query with per-feature weights on the fp32 embeddings
     "q1w": dict(n=1_000_000, D=768, Q=1, k=100, metric="cosine", weighted=True, dtype="fp32"),
     "q1": dict(n=1_000_000, D=768, Q=1, k=100, metric="cosine"),
+    "q1wb": dict(n=1_000_000, D=768, Q=1, k=100, metric="cosine", weighted=True),          # the same on a bf16 bank
     "q4": dict(n=1_000_000, D=768, Q=4, k=100, metric="cosine"),
     # BASELINE configs[2] ("C3"): 10M-vector bank, 4096-query batch, L2 (= unweighted MSE), tensor-pipe bound
     "c3": dict(n=10_000_000, D=768, Q=4096, k=100, metric="MSE", steps=10),
@@ -61,7 +62,7 @@ WORKLOADS = {
     # query, combine = min; 1M bank rows = 15625 items
     "l64": dict(n=1_000_000, D=768, Q=1, k=100, metric="cosine", weighted=True, dtype="fp32", L=64),
 }
-PIXEL_WORKLOADS = {"c5": (1_000_000, 4, 100), "c5s": (100_000, 4, 100), "c5q1": (1_000_000, 1, 100)}
+PIXEL_WORKLOADS = {"c5": (1_000_000, 4, 100), "c5s": (100_000, 4, 100), "c5q1": (1_000_000, 1, 100), "c5q1s": (100_000, 1, 100)}
 ALSO_N1 = ["c2w", "q1w", "c3", "c5q1"]
 ALSO_MULTI = ["c3", "c4"]
 KNOBS = ("SKY_TC_DEBUG", "SKY_TC_STAGES", "SKY_TC_GRID", "SKY_TC_POLICY", "SKY_TW_DEBUG", "SKY_TB_DEBUG", "SKY_TB_PHASE0",

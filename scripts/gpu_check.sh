@@ -2,8 +2,8 @@
 # round 2: targeted GPU tests after a change + a few bench lines
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_cli.py tests/test_gpu_ingest.py tests/test_properties.py tests/test_gpu_exchange.py tests/test_gpu_c1_real.py -m gpu -q --timeout 900 -p no:cacheprovider > gpurun_out/pytest_check.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_check.log | cut -c1-200
-for wl in q1w c2; do
+timeout -k 10 900 python -m pytest tests/test_gpu_exchange.py tests/test_gpu_c1_real.py tests/test_gpu_integration_stub.py -m gpu -v --timeout 300 --timeout-method=thread -p no:cacheprovider > gpurun_out/pytest_check.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_check.log | cut -c1-200
+for wl in c3g8; do
 timeout 300 python bench.py --workload $wl --also none --no-cpu > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; echo "bench $wl rc=$?"; tail -2 gpurun_out/bench_$wl.err
 python - $wl <<'PY'
 import json, sys

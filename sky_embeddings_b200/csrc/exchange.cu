@@ -83,8 +83,14 @@ xchg_merge_kernel(const unsigned char* __restrict__ local, int world, size_t slo
     const int q = blockIdx.x, tid = threadIdx.x;
     if (tid < world) {
         const unsigned* f = reinterpret_cast<const unsigned*>(local + flag_off(slot_units, world, max_Q, parity, tid)) + q;
-        // sequence numbers only grow; a peer that is one search ahead has already overwritten nothing of this parity
-        while (static_cast<int>(ld_acquire_sys_u32(f) - seq) < 0) __nanosleep(64);
+        // sequence numbers only grow; a peer that is one search ahead has already overwritten nothing of this parity.
+        // A peer that never arrives (crashed rank, mismatched call counts) must not hang the GPU for ever: after ~10 s
+        // the kernel traps, which surfaces as a CUDA error on the next call of this process.
+        const long long t_end = clock64() + 20000000000ll;
+        while (static_cast<int>(ld_acquire_sys_u32(f) - seq) < 0) {
+            __nanosleep(64);
+            if (clock64() > t_end) __trap();
+        }
     }
     __syncthreads();
     const size_t nq = static_cast<size_t>(Q) * k;

@@ -79,11 +79,14 @@ def test_exchange_rejects_bad_use():
     lib.sky_exchange_destroy(h)
 
 
-@pytest.mark.parametrize("metric,weighted,Q,k", [("cosine", False, 64, 100), ("MSE", True, 16, 10), ("cosine", True, 3, 20), ("MSE", False, 300, 50)])
-def test_fused_sharded_search_equals_unsharded(metric, weighted, Q, k):
+@pytest.mark.parametrize("metric,weighted,Q,k,path", [("cosine", False, 64, 100, "auto"), ("MSE", True, 16, 10, "auto"),
+                                                      ("cosine", True, 3, 20, "auto"), ("MSE", False, 32, 50, "batch")])
+def test_fused_sharded_search_equals_unsharded(metric, weighted, Q, k, path):
     """sky_search_sharded on two shards of one bank (two logical ranks on one GPU, two streams): the shard merge kernel
     delivers into both exchange buffers, the flag-waiting merge returns the global top-k -- identical, bit for bit, to
-    the search over the unsharded bank; K1 / K2 / K2w2 deliver fused, K2b (Q = 300) through the push kernel."""
+    the search over the unsharded bank; K1 / K2 / K2w2 deliver fused, K2b (path="batch") through the push kernel.
+    Q stays small here: with both ranks on ONE GPU the first rank's waiting merge CTAs share the SMs with the second
+    rank's scorer, and hundreds of them would leave it no room (one process per GPU has no such coupling)."""
     from sky_embeddings_b200 import Bank, synth
     from sky_embeddings_b200 import _lib as L
     dev = torch.device("cuda:0")
@@ -106,15 +109,22 @@ def test_fused_sharded_search_equals_unsharded(metric, weighted, Q, k):
     if weighted:
         w = (torch.rand(Q, D, generator=g) + 0.25).to(dev)
         w = (w / w.sum(1, keepdim=True)).contiguous()
-    want_s, want_i = full.search(t, w, k=k, metric=metric)
+    want_s, want_i = full.search(t, w, k=k, metric=metric, path=path)
     lib, hs = _mk(2, Q, k, dev)
     streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    # Two ranks in ONE process share one host thread and one CUDA context: rank 0's merge kernel spins on the GPU until
+    # rank 1's kernels have run, so nothing on rank 1's launch path may synchronise the device (a first-use workspace
+    # allocation or module load would).  One ordinary search per shard warms all of that up; outputs are preallocated.
+    # (One process per GPU -- the real deployment -- has no such coupling.)
+    outs = []
+    for b, lo in shards:
+        b.search(t, w, k=k, metric=metric, idx_offset=lo, path=path)
+        outs.append((torch.empty(Q, k, device=dev), torch.empty(Q, k, dtype=torch.int64, device=dev)))
     for it in range(3):
-        outs = []
         torch.cuda.synchronize()
         for r, (b, lo) in enumerate(shards):
             with torch.cuda.stream(streams[r]):
-                outs.append(b.search_sharded(hs[r], t, w, k=k, metric=metric, idx_offset=lo))
+                b.search_sharded(hs[r], t, w, k=k, metric=metric, path=path, idx_offset=lo, out_scores=outs[r][0], out_idx=outs[r][1])
         torch.cuda.synchronize()
         for r in range(2):
             assert torch.equal(outs[r][1], want_i), f"iteration {it} rank {r}: indices differ from the unsharded search"
