@@ -468,10 +468,16 @@ def run_search_workload(name, wl, args, dev, steps, warmup, strong, headline):
     ms_total = ev0.elapsed_time(ev1)
     n_kern, kern_ms = bank.profile_read(reset=True)
     bank.profile(False)
+    kernel_ms_ranks = None
     if world > 1:
         tt = torch.tensor([ms_total], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
+        # the scoring kernel's mean duration on every rank: a synchronous exchange makes each step as slow as the slowest
+        kk = torch.tensor([kern_ms / max(n_kern, 1) * (n_kern / steps)], device=dev)
+        allk = [torch.empty_like(kk) for _ in range(world)]
+        dist.all_gather(allk, kk)
+        kernel_ms_ranks = [round(float(v.item()), 4) for v in allk]
     ms_step = ms_total / steps
 
     # end-to-end through the host-buffer API
@@ -509,7 +515,7 @@ def run_search_workload(name, wl, args, dev, steps, warmup, strong, headline):
                "warmup": max(warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                "config": workload_config(name, wl, world, strong),
-               "exchange": (args.exchange if world > 1 else None),
+               "exchange": (args.exchange if world > 1 else None), "kernel_ms_per_rank": kernel_ms_ranks,
                "value_definition": "Q / step time over the global (row-sharded) bank" if (strong or world == 1) else
                                    "N_gpus * Q / step time (query-over-1M-vector-shard searches/s, weak scaling)",
                "qps_global_bank": agg, "parity": parity, "clocks": sampler.summary((t_wall0, t_wall1)),

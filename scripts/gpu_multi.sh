@@ -26,7 +26,7 @@ PY
 }
 run c2_peer --steps 200 --warmup 10 --no-cpu --also none --exchange peer
 run c2_nccl --steps 200 --warmup 10 --no-cpu --also none --exchange nccl
-run c2w_peer --workload c2w --steps 100 --warmup 10 --no-cpu --also none --exchange peer
+[ "$N" -le 2 ] && run c2w_peer --workload c2w --steps 100 --warmup 10 --no-cpu --also none --exchange peer
 if [ "${FULL:-0}" = "1" ]; then
   run default_peer --no-cpu --exchange peer
 fi

@@ -159,8 +159,17 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
             tv = p.t[static_cast<size_t>(p.q0 + q) * p.D + d];
             wv = p.w ? p.w[static_cast<size_t>(p.q0 + q) * p.D + d] : 1.0f;
         }
-        sA[i] = (COS && WEIGHTED) ? wv * tv : tv;
-        sW[i] = wv;
+        // Inside a 64-element k-block a lane owns CPL consecutive elements and reads them as CPL / 4 128-bit loads.  With
+        // CPL = 8 (bf16 bank) the natural order puts the lanes' loads 32 bytes apart: lanes lc and lc + 4 hit the same
+        // banks (2-way conflict on every query load, 12 M conflict cycles per 1 M-row search in ncu).  Store half h of
+        // every lane contiguously instead: element lc*8 + h*4 + e -> position h*32 + lc*4 + e.
+        int pi = i;
+        if constexpr (CPL == 8) {
+            const int e64 = d & 63;
+            pi = q * Dp + (d & ~63) + ((e64 >> 2) & 1) * 32 + (e64 >> 3) * 4 + (e64 & 3);
+        }
+        sA[pi] = (COS && WEIGHTED) ? wv * tv : tv;
+        sW[pi] = wv;
     }
     // the float mirror of the threshold starts as NaN: every comparison fails, so everything passes the pre-filter
     if (tid < QC) { sThr[tid] = (tid < p.nq) ? 0ull : ~0ull; sThrF[tid] = __uint_as_float(0x7FC00000u); sCnt[tid] = 0; sLmax[tid] = 0; }
@@ -168,13 +177,14 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
     if (warp < QC) {
         double acc = 0.0;
         for (int d = lane; d < p.D; d += 32) {
+            // (from global memory: the shared-memory copies may be stored in a permuted order)
+            const float wv = (warp < p.nq) ? (p.w ? p.w[static_cast<size_t>(p.q0 + warp) * p.D + d] : 1.0f) : 0.f;
             if (COS) {
                 // w t^2 (the reference squares t after the product with w: weights * target ** 2)
-                const float wv = sW[warp * Dp + d];
                 const float tv = (warp < p.nq) ? p.t[static_cast<size_t>(p.q0 + warp) * p.D + d] : 0.f;
                 acc += static_cast<double>(wv * (tv * tv));
             } else {
-                acc += static_cast<double>(sW[warp * Dp + d]);
+                acc += static_cast<double>(wv);
             }
         }
 #pragma unroll
@@ -256,7 +266,9 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
         const int lr = lane / LPR, lc = lane % LPR;
         const uint32_t stage0 = ptx::smem_u32(sStage);
         const uint32_t my_off = static_cast<uint32_t>((warp * RPW + lr) * ROWB + lc * 16);
-        const uint32_t sA_addr = ptx::smem_u32(sA) + lc * CPL * 4, sW_addr = ptx::smem_u32(sW) + lc * CPL * 4;
+        // lane lc's h-th 128-bit piece of a query k-block: at lc*16 + h*HSTEP (see the staging loop)
+        constexpr int HSTEP = (CPL == 8) ? 128 : 16;
+        const uint32_t sA_addr = ptx::smem_u32(sA) + lc * 16, sW_addr = ptx::smem_u32(sW) + lc * 16;
         const float invD = 1.0f / static_cast<float>(p.D);
         const int L = p.L;
         int stage = 0;
@@ -322,11 +334,11 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
                     uint64_t a2[NP], w2[NP];
 #pragma unroll
                     for (int h = 0; h < NP / 2; ++h) {
-                        const uint4 av = lds128(sA_addr + q * Dp * 4 + qoff + h * 16);
+                        const uint4 av = lds128(sA_addr + q * Dp * 4 + qoff + h * HSTEP);
                         a2[2 * h] = (static_cast<uint64_t>(av.y) << 32) | av.x;
                         a2[2 * h + 1] = (static_cast<uint64_t>(av.w) << 32) | av.z;
                         if (WEIGHTED) {
-                            const uint4 wv = lds128(sW_addr + q * Dp * 4 + qoff + h * 16);
+                            const uint4 wv = lds128(sW_addr + q * Dp * 4 + qoff + h * HSTEP);
                             w2[2 * h] = (static_cast<uint64_t>(wv.y) << 32) | wv.x;
                             w2[2 * h + 1] = (static_cast<uint64_t>(wv.w) << 32) | wv.z;
                         }

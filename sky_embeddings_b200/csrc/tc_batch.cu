@@ -409,15 +409,15 @@ __global__ void batch_bounds_kernel(const uint64_t* __restrict__ tauc, const flo
 // carry[q][kpad] (running top-k as composites, 0 = empty) + the P lists of this phase -> new carry, tauc;
 // resets the lists.  last != 0: also writes the final (score, index) rows.
 constexpr int kMpThreads = 256;
-constexpr int kMpSample = 4096;
+constexpr int kMpSample = 4096;      // first (dense) phase; later phases run with a small pool and sample (more CTAs per SM)
 __global__ void __launch_bounds__(kMpThreads)
 merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, const uint64_t* __restrict__ lists,
-                   int* __restrict__ counts, uint64_t* __restrict__ lthr, int P, int Qp, int cap, int k, int kpad, int kMpPool, int largest,
+                   int* __restrict__ counts, uint64_t* __restrict__ lthr, int P, int Qp, int cap, int k, int kpad, int kMpPool, int nsample, int largest,
                    int last, int nq, int64_t idx_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
     uint64_t* pool = sel + kpad;                              // [kMpPool]
-    uint64_t* extra = pool + kMpPool;                         // [kMpSample] survivors of the sampled pre-select
+    uint64_t* extra = pool + kMpPool;                         // [nsample] survivors of the sampled pre-select
     __shared__ uint32_t hist[256];
     __shared__ uint32_t scratch[4];
     __shared__ uint32_t npool;
@@ -477,21 +477,21 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
         if (tau0 != 0) {
             for (int j = tid; j < k; j += kMpThreads) {
                 const uint64_t v = cq[j];
-                if (v >= tau0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < kMpSample) extra[pos] = v; }
+                if (v >= tau0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < static_cast<uint32_t>(nsample)) extra[pos] = v; }
             }
             for (int p = warp; p < P; p += nwarps) {
                 const int n = s_n[p];
                 const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
                 for (int i = lane; i < n; i += 32) {
                     const uint64_t v = e[i];
-                    if (v >= tau0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < kMpSample) extra[pos] = v; }
+                    if (v >= tau0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < static_cast<uint32_t>(nsample)) extra[pos] = v; }
                 }
             }
             __syncthreads();
             if (nkeep <= kRankSortMax) {
                 block_rank_topk(extra, static_cast<int>(nkeep), k, kpad, sel);
                 done = true;
-            } else if (nkeep <= kMpSample) {
+            } else if (nkeep <= static_cast<uint32_t>(nsample)) {
                 block_select_sort([&](int j) { return extra[j]; }, static_cast<int>(nkeep), k, kpad, sel, hist, scratch);
                 done = true;
             }
@@ -617,7 +617,8 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     int t0 = 0;
     int per_cta = 1;
     bool first = true;
-    int growth = 4;       // phase sizes 1, 1, 4, 16, ... tiles per CTA: fewer merges, a few more survivors per phase
+    int growth = 4;       // phase sizes 1, 1, 4, 16, ... tiles per CTA (measured: growth 16 saves two merges on a small shard but its
+                          // k ln 17 survivors per query overflow lists and pools at k = 1000: C4's share 20 -> 29 ms)
     { const int e = env_knob("SKY_TB_PHASE0", 0); if (e >= 1) per_cta = e; }
     { const int e = env_knob("SKY_TB_GROWTH", 0); if (e >= 2) growth = e; }
     while (t0 < num_tiles) {
@@ -637,14 +638,18 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
         const int last = t1 == num_tiles ? 1 : 0;
         // sample pool of the merge: large enough that the k-th best of the sample keeps fewer than kMpSample of
         // all candidates (first phase: every row of the phase's tiles is one)
-        int pool = 4096;
+        // later phases see k carried entries plus ~k ln 5 survivors: a pool of max(2048, 4 kpad) holds them (a phase
+        // that overflows it falls back to the exact select over L2), and the small footprint lets 8 merge CTAs share an
+        // SM instead of 3 -- on small shards the per-phase merges are a fifth of the search
+        int pool = 4 * kpad > 2048 ? 4 * kpad : 2048, nsample = 2 * kpad > 1024 ? 2 * kpad : 1024;
         if (first) {
             const int64_t np_max = static_cast<int64_t>(grid) * kTileRows + k;
             const int64_t want = round_up(2 * np_max * k / kMpSample, 1024);
             pool = static_cast<int>(want < 4096 ? 4096 : (want > 16384 ? 16384 : want));
+            nsample = kMpSample;
         }
-        const size_t msmem = static_cast<size_t>(kpad + pool + kMpSample) * 8;
-        merge_phase_kernel<<<Qp, kMpThreads, msmem, st>>>(carry, tauc, lists, counts, lthr, P, Qp, cap, k, kpad, pool,
+        const size_t msmem = static_cast<size_t>(kpad + pool + nsample) * 8;
+        merge_phase_kernel<<<Qp, kMpThreads, msmem, st>>>(carry, tauc, lists, counts, lthr, P, Qp, cap, k, kpad, pool, nsample,
                                                          metric_largest(metric) ? 1 : 0, last, Q, idx_offset, out_scores, out_idx);
         SKY_LAUNCH_CHECK("merge_phase_kernel");
         t0 = t1;
