@@ -41,6 +41,7 @@ struct TcParams {
     int num_tiles, kblocks, stages, metric;
     unsigned long long bank_policy;   // L2 cache hint of the bank stream
     int debug;              // bit0: epilogue skips scoring, bit1: MMA skipped, bit2: contiguous tiles (experiments)
+    int use_tma;            // bank stages by one TMA box load each (else 1024 16-byte cp.async by 128 threads)
     float inv_dd;           // 1 / D^2
 };
 
@@ -69,7 +70,7 @@ __device__ unsigned long long g_epi[64 * 12];   // per-tile stamps inside the ep
 
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
+tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment is required by the 128-byte swizzle atoms
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -111,7 +112,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_q);
-        for (int s = 0; s < S; ++s) { ptx::mbar_init(&full_bar[s], kProducerThreads); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < S; ++s) { ptx::mbar_init(&full_bar[s], p.use_tma ? 1 : kProducerThreads); ptx::mbar_init(&empty_bar[s], 1); }
+        if (p.use_tma) ptx::prefetch_tmap(&tmap_bank);
         ptx::mbar_init(b_full, 1);
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
         ptx::fence_barrier_init();
@@ -151,6 +153,24 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
             for (int kb = 0; kb < KB; ++kb)
                 ptx::tma_load_2d(&tmap_q, sB + static_cast<size_t>(kb) * BN * 128, b_full, kb * kKBlock, 0, ptx::kEvictLast);
         }
+        if (p.use_tma) {
+            // one thread, one TMA box per stage: the tile-major bank is a [rows * KB, 64] tensor whose 128-row boxes are
+            // the contiguous 16 KB (tile, k-block) pieces; the TMA unit applies the 128-byte swizzle on the way in
+            if (tid == 0) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int tile = tile_of(it);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        ptx::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                        ptx::tma_load_2d(&tmap_bank, sA + static_cast<size_t>(stage) * kStageBytes, &full_bar[stage], 0,
+                                         (tile * KB + kb) * kTileRows, p.bank_policy);
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else {
         uint32_t dst_off[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -175,6 +195,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
                 src += kStageBytes;
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
+        }
         }
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
@@ -480,6 +501,7 @@ int launch_pack_queries(const float* t, int Q, int D, int Dp, int q_pad, int met
 }
 
 constexpr int kTcBN = 64;
+constexpr int kTcUseTma = 0;      // bank stream of K2: 0 = cp.async producers, 1 = TMA boxes (measured)
 
 static size_t tc_tail_bytes(int BN) {
     return (2 * kMaxStages + 1 + 4) * sizeof(uint64_t) + 16 + BN * (8 + 4 + 4 + 4 + 4) + 4 * 256 * 4 + 16;
@@ -556,7 +578,8 @@ int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const Searc
           p.bank_policy = pv == 1 ? 0x1000000000000000ull /* evict normal */ : (pv == 2 ? ptx::kEvictLast : ptx::kEvictFirst); }
         p.inv_dd = 1.0f / (static_cast<float>(b->D) * static_cast<float>(b->D));
         prof_mark(b, st);
-        tc_search_kernel<BN><<<grid, kTcThreads, smem, st>>>(tmq, p);
+        p.use_tma = (b->tmap_ready && env_knob("SKY_TC_TMA", kTcUseTma) != 0) ? 1 : 0;
+        tc_search_kernel<BN><<<grid, kTcThreads, smem, st>>>(tmq, b->tmap_bank, p);
         prof_mark(b, st);
         SKY_LAUNCH_CHECK("tc_search_kernel");
     }
