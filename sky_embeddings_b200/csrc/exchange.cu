@@ -34,6 +34,7 @@ struct sky_exchange {
 namespace sky {
 
 constexpr int kXchgThreads = 256;
+constexpr int kXchgSortedMax = 20480;     // candidates of one query held in shared memory (160 KB) for the sorted merge
 
 struct PeerPtrs { unsigned char* base[kMaxPeers]; };
 
@@ -107,10 +108,12 @@ xchg_merge_kernel(const unsigned char* __restrict__ local, int world, size_t slo
         if (__ldcg(reinterpret_cast<const long long*>(src_i(j))) < 0) return 0ull;
         return make_composite(score_to_key(__ldcg(src_s(j)), largest != 0), static_cast<uint32_t>(j));
     };
-    if (n <= kRankSortMax) {
+    if (n <= kXchgSortedMax) {
+        // every shard's list is sorted best-first (lower index first among equal scores, and shards hold increasing row
+        // ranges): rank by binary search across the lists
         for (int j = tid; j < n; j += kXchgThreads) cand[j] = fetch(j);
         __syncthreads();
-        block_rank_topk(cand, n, k_out, kpad, sel);
+        block_merge_sorted(cand, world, k, k_out, kpad, sel);
     } else {
         block_select_sort(fetch, n, k_out, kpad, sel, hist, scratch);
     }
@@ -171,7 +174,7 @@ int launch_xchg_merge(const XchgTarget& xt, int Q, int k, int k_out, int metric,
     DeviceGuardX g(device);
     const int kpad = next_pow2_x(k_out);
     const int n = xt.world * k;
-    const size_t smem = static_cast<size_t>(kpad + (n <= kRankSortMax ? n : 0)) * sizeof(uint64_t);
+    const size_t smem = static_cast<size_t>(kpad + (n <= kXchgSortedMax ? n : 0)) * sizeof(uint64_t);
     SKY_CUDA(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     xchg_merge_kernel<<<Q, kXchgThreads, smem, st>>>(xt.base[xt.rank], xt.world, xt.slot_units, xt.max_Q, xt.parity, xt.seq, Q, k, k_out, kpad,
                                                     metric_largest(metric) ? 1 : 0, out_scores, out_idx);

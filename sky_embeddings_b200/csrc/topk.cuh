@@ -405,4 +405,35 @@ __device__ __forceinline__ void block_rank_topk(const uint64_t* cand, int n, int
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Block-level merge of R lists that are each sorted best-first (composites strictly decreasing, 0 = empty tail), held
+// in shared memory as cand[R][k_in]: the global rank of an element is its position in its own list plus, for every
+// other list, the number of elements there that beat it -- R - 1 binary searches instead of the R * k_in comparisons
+// of the rank sort.  This is the shard merge of a sharded search (every shard's result is sorted by construction).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_merge_sorted(const uint64_t* cand, int R, int k_in, int k_out, int kpad, uint64_t* sel) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = tid; j < kpad; j += nt) sel[j] = 0;
+    __syncthreads();
+    const int n = R * k_in;
+    for (int idx = tid; idx < n; idx += nt) {
+        const uint64_t v = cand[idx];
+        if (v == 0) continue;
+        const int r = idx / k_in;
+        int rank = idx - r * k_in;
+        for (int o = 0; o < R && rank < k_out; ++o) {
+            if (o == r) continue;
+            const uint64_t* lst = cand + o * k_in;
+            int lo = 0, hi = k_in;                 // first position whose element does not beat v
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (lst[mid] > v) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k_out) sel[rank] = v;
+    }
+    __syncthreads();
+}
+
 }  // namespace sky
