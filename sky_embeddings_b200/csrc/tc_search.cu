@@ -5,9 +5,11 @@
 //   cosine :163-170   s = t.z / (|t| |z| + 1e-6)            |z|^2 = row norm stored with the bank
 //   MSE    :188-192   s = (|t|^2 - 2 t.z + |z|^2) / D^2     (rank-equivalent to L2)
 // One persistent CTA per SM.  Warp roles:
-//   warps 0-3   bank stream: 128 threads copy each contiguous 16 KB (tile, k-block) piece with 16-byte cp.async
-//               into the 128-byte-swizzled ring stage; thread 0 also loads the query matrix B[BN, Dp] once by
-//               TMA (resident in shared memory for the whole kernel)
+//   warps 0-3   bank stream: thread 0 lands each contiguous 16 KB (tile, k-block) piece with ONE TMA box load
+//               (128-byte swizzle applied by the TMA unit) and loads the query matrix B[BN, Dp] once by TMA
+//               (resident in shared memory for the whole kernel); the other producer threads idle.  The round-1
+//               stream (128 threads x 8 16-byte cp.async per stage) is kept behind use_tma = 0: it measured
+//               3 % slower on BASELINE config 2 (0.2518 vs 0.2447 ms)
 //   warps 4-7   epilogue: tcgen05.ld accumulators -> conservative pre-filter bitmask -> exact insert of survivors
 //   warp 8      MMA issuer (one thread): tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM, two accumulator
 //               stages so the epilogue of tile i overlaps the MMAs of tile i+1
@@ -501,7 +503,7 @@ int launch_pack_queries(const float* t, int Q, int D, int Dp, int q_pad, int met
 }
 
 constexpr int kTcBN = 64;
-constexpr int kTcUseTma = 0;      // bank stream of K2: 0 = cp.async producers, 1 = TMA boxes (measured)
+constexpr int kTcUseTma = 1;      // bank stream of K2: 1 = one TMA box per stage (measured 0.2447 ms on C2), 0 = 1024 cp.async per stage (0.2518 ms)
 
 static size_t tc_tail_bytes(int BN) {
     return (2 * kMaxStages + 1 + 4) * sizeof(uint64_t) + 16 + BN * (8 + 4 + 4 + 4 + 4) + 4 * 256 * 4 + 16;
