@@ -58,6 +58,7 @@ WORKLOADS = {
     # the per-GPU shares of C3 / C4 at 8 GPUs as single-GPU workloads (kernel experiments)
     "c3g8": dict(n=1_250_000, D=768, Q=4096, k=100, metric="MSE", steps=20),
     "c4g8": dict(n=12_500_000, D=768, Q=1000, k=1000, metric="cosine", steps=5),
+    "c4g2": dict(n=50_000_000, D=768, Q=1000, k=1000, metric="cosine", steps=3),      # 76.8 GB of bank on one GPU
     # the reference's production call (scripts/done/sim.sh: -mp False): 64 patch tokens per item, one weighted
     # query, combine = min; 1M bank rows = 15625 items
     "l64": dict(n=1_000_000, D=768, Q=1, k=100, metric="cosine", weighted=True, dtype="fp32", L=64),
@@ -195,7 +196,7 @@ def make_queries(n_total, D, Q, dev, weighted, gen_seed=1234):
         c, off = divmod(r, synth.CHUNK_ROWS)
         if c not in cache:
             cache = {c: raw_chunk(c, min(synth.CHUNK_ROWS, n_total - c * synth.CHUNK_ROWS), D, dev)}
-        rows.append(cache[c][off])
+        rows.append(cache[c][off].clone())          # a copy: a view would keep the whole 200 MB chunk alive (1000 chunks at C4)
     z = (torch.stack(rows) - mu) / (sd + 1e-8)
     gen = torch.Generator(device=dev).manual_seed(gen_seed)
     t = z + 0.1 * torch.randn((Q, D), generator=gen, device=dev)
@@ -731,7 +732,11 @@ def run_gpu(args):
         except AssertionError:
             raise                                            # a parity gate failed: no bench line at all
         except torch.cuda.OutOfMemoryError as e:
-            rec = {"skipped": f"out of device memory: {str(e)[:120]}"}
+            free_b, total_b = torch.cuda.mem_get_info(dev)
+            rec = {"skipped": f"out of device memory: {str(e)[:120]}",
+                   "memory": {"free_GB": round(free_b / 1e9, 2), "total_GB": round(total_b / 1e9, 2),
+                              "torch_allocated_GB": round(torch.cuda.memory_allocated(dev) / 1e9, 2),
+                              "torch_reserved_GB": round(torch.cuda.memory_reserved(dev) / 1e9, 2)}}
         except _lib.SkyError as e:
             if e.code != -4:                                 # SKY_ERR_NOMEM
                 raise
