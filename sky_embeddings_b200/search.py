@@ -100,16 +100,38 @@ def build_encoder(args, config, root, device):
     return model, config
 
 
-def load_tiles(test_dirs):
-    """Tile mode input: ``*.npy`` tiles [C, H, W] (NaN planes for missing bands).  FITS needs astropy, which is the
-    reference's dependency, not this package's: with it installed, convert with the reference's load_fits_bands."""
+def load_tiles(test_dirs, config=None):
+    """Tile mode input.  Directories of `[calexp-]HSC-<band>-<tract>-<patch>.fits` files are grouped per patch and read
+    like the reference does (find_HSC_bands / load_fits_bands, utils/dataloaders.py:330-437: bands and min_bands from the
+    model's config, NaN planes for missing bands, ra / dec from the first band's TAN WCS) by the built-in FITS reader
+    (`fitslite`: uncompressed image HDUs); `*.npy` tiles [C, H, W] are taken as they are (no WCS).  Tiles are opened
+    lazily, one per loader item."""
+    from . import fitslite  # noqa: PLC0415
     from .ingest import load_tile_npy  # noqa: PLC0415
-    paths = []
+    bands, min_bands, use_calexp = ['G', 'R', 'I', 'Z', 'Y'], 5, True
+    if config is not None and config.has_section('DATA'):
+        if 'bands' in config['DATA']:
+            bands = ast.literal_eval(config['DATA']['bands'])
+        if 'min_bands' in config['DATA']:
+            min_bands = int(config['DATA']['min_bands'])
+        if 'use_calexp' in config['DATA']:
+            use_calexp = str2bool(config['DATA']['use_calexp'])
+    groups = fitslite.find_tile_bands(test_dirs, bands, min_bands, use_calexp=use_calexp, verbose=1)
+    npys = []
     for d in test_dirs:
-        paths += sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".npy"))
-    if not paths:
-        raise SystemExit(f"no .npy tiles under {test_dirs}")
-    return [load_tile_npy(p) for p in paths]
+        npys += sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".npy"))
+    if not groups and not npys:
+        raise SystemExit(f"no FITS patches with at least {min_bands} of {bands} and no .npy tiles under {test_dirs}")
+
+    class LazyTiles:
+        def __len__(self):
+            return len(groups) + len(npys)
+
+        def __getitem__(self, i):
+            if i < len(groups):
+                return fitslite.load_tile_bands(groups[i], return_wc=True)
+            return load_tile_npy(npys[i - len(groups)])
+    return LazyTiles()
 
 
 def main(argv=None):
@@ -143,7 +165,7 @@ def main(argv=None):
     target_src = ingest.H5Cutouts(os.path.join(data_dir, target_fn), img_size=img_size)
     target_loader = target_src.loader(indices=target_indices, batch_size=args.batch_size)
     if tiles_mode:
-        test_loader = ingest.TileLoader(load_tiles(args.test_dirs), batch_size=args.batch_size, img_size=img_size,
+        test_loader = ingest.TileLoader(load_tiles(args.test_dirs, config), batch_size=args.batch_size, img_size=img_size,
                                         overlap=args.overlap, device=device)
         test_src = None
     else:

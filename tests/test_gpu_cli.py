@@ -85,3 +85,30 @@ def test_cli_tile_mode_writes_the_sky_sim_search_layout(tmp_path):
     assert sorted(r.files) == sorted(KEYS)
     assert r["target_images"].shape == (2 * 65, 5, 64, 64), "each target is followed by its 64 augmented copies"
     assert r["test_scores"].shape == (20,) and np.all(np.diff(r["test_scores"]) <= 0) and np.isfinite(r["test_scores"]).all()
+
+
+def test_cli_tile_mode_reads_fits_tiles(tmp_path):
+    """-tst_dirs over a directory of per-band FITS files (the reference's naming): patches are grouped, a missing band
+    becomes a NaN plane, ra / dec come from the header's TAN WCS, and the best match of a target cut from a tile is found
+    at the sky position of that cutout."""
+    from sky_embeddings_b200 import fitslite, h5lite, ingest, search, synth
+    hdr = {"CTYPE1": "RA---TAN", "CTYPE2": "DEC--TAN", "CRVAL1": 150.25, "CRVAL2": 2.5, "CRPIX1": 101.0, "CRPIX2": 81.0,
+           "CD1_1": -4.6e-5, "CD1_2": 0.0, "CD2_1": 0.0, "CD2_2": 4.6e-5}
+    tiles = tmp_path / "tiles"
+    tiles.mkdir()
+    planes = synth.cutouts(1, 5, 200, 200, stream=90, nan_frac=0.0, nan_chan_p=0.0)[0]
+    for i, b in enumerate("GRIZY"):
+        fitslite.write_image(str(tiles / f"calexp-HSC-{b}-9813-4,4.fits"), planes[i], hdr)
+    coords = ingest.generate_overlap_coords((200, 200), 64, 0.4)
+    h0, w0 = coords[5]
+    tgt = planes[None, :, h0:h0 + 64, w0:w0 + 64].copy()
+    data = tmp_path / "data"
+    data.mkdir()
+    h5lite.write_h5(str(data / "targets.h5"), dict(cutouts=tgt, ra=np.zeros(1, "f"), dec=np.zeros(1, "f")))
+    out = search.main(["stubmodel", "-tgt_fn", "targets.h5", "-tst_dirs", str(tiles), "-tgt_i", "[0]", "-aug", "False", "-mp", "True",
+                       "-bs", "4", "-ns", "5", "-dd", str(data), "--results-dir", str(tmp_path / "results"),
+                       "--encoder", "tests.test_gpu_cli:stub_factory"])
+    r = np.load(out)
+    ra, dec = fitslite.TanWcs(hdr).all_pix2world([h0 + 32], [w0 + 32], 0)        # argument order as the reference calls it
+    assert np.allclose(r["test_ra_decs"][0], [ra[0], dec[0]], atol=1e-4), "top hit is the cutout the target was cut from"
+    assert np.array_equal(r["test_images"][0], np.maximum(tgt[0], -3.0))
