@@ -2,8 +2,8 @@
 # round 2: targeted GPU tests after a change + a few bench lines
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout -k 10 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_properties.py -m gpu -q -k "batch or fullsize or tensor_paths or merge or golden or stream or multi_query or l64 or patches" --timeout 400 --timeout-method=thread -p no:cacheprovider > gpurun_out/pytest_check.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_check.log | cut -c1-200
-for wl in c3g8 c4g8 q1wb q1 q4; do
+timeout -k 10 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_properties.py tests/test_gpu_cli.py -m gpu -q -k "batch or fullsize or tensor_paths or merge or cli_tile" --timeout 400 --timeout-method=thread -p no:cacheprovider > gpurun_out/pytest_check.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_check.log | cut -c1-200
+for wl in c3g8 c3; do
 timeout 400 python bench.py --workload $wl --also none --no-cpu > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; echo "bench $wl rc=$?"; tail -2 gpurun_out/bench_$wl.err
 python - $wl <<'PY'
 import json, sys

@@ -413,7 +413,9 @@ constexpr int kMpSample = 4096;      // first (dense) phase; later phases run wi
 __global__ void __launch_bounds__(kMpThreads)
 merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, const uint64_t* __restrict__ lists,
                    int* __restrict__ counts, uint64_t* __restrict__ lthr, int P, int Qp, int cap, int k, int kpad, int kMpPool, int nsample, int largest,
-                   int last, int nq, int64_t idx_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+                   int last, int nq, int64_t idx_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+                   const unsigned char* __restrict__ only) {
+    if (only && !only[blockIdx.x]) return;        // this query was merged by the warp-per-query kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
     uint64_t* pool = sel + kpad;                              // [kMpPool]
@@ -524,6 +526,100 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
     }
 }
 
+// Warp-per-query merge of one LATER phase (k <= 128): the carry is sorted, the phase's survivors are few (~k ln 5 per
+// query), so one warp ranks them with binary searches instead of a 256-thread CTA paying six dependent L2 round trips
+// per query -- eight queries per CTA, one wave over the GPU.  A query with more survivors than a warp holds is flagged
+// in `slow` and left (untouched) to merge_phase_kernel.
+constexpr int kMwWarps = 8;
+constexpr int kMwMaxM = 256;
+constexpr int kMwMaxK = 128;
+constexpr int kMwMaxPL = 8;          // lists per lane: P <= 256
+__global__ void __launch_bounds__(kMwWarps * 32)
+merge_phase_warp_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, const uint64_t* __restrict__ lists,
+                        int* __restrict__ counts, uint64_t* __restrict__ lthr, unsigned char* __restrict__ slow, int P, int Qp, int cap,
+                        int k, int kpad, int largest, int last, int nq, int64_t idx_offset, float* __restrict__ out_scores,
+                        int64_t* __restrict__ out_idx) {
+    __shared__ uint64_t sS[kMwWarps][kMwMaxM];      // survivors as gathered
+    __shared__ uint64_t sT[kMwWarps][kMwMaxM];      // survivors, best first
+    __shared__ uint64_t sC[kMwWarps][kMwMaxK];      // carry of the earlier phases (best first, zeros behind)
+    __shared__ uint64_t sN[kMwWarps][kMwMaxK];      // new carry
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.x * kMwWarps + w;
+    if (q >= Qp) return;
+    // fills of this query's P lists: lane owns lists lane, lane + 32, ...
+    int cnt[kMwMaxPL];
+    int mine = 0;
+#pragma unroll
+    for (int i = 0; i < kMwMaxPL; ++i) {
+        const int p = lane + 32 * i;
+        cnt[i] = p < P ? ld_cg_i32(counts + static_cast<size_t>(p) * Qp + q) : 0;
+        mine += cnt[i];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+    const int m = __shfl_sync(0xffffffffu, incl, 31);
+    if (m > kMwMaxM) {
+        if (lane == 0) slow[q] = 1;
+        return;
+    }
+    if (lane == 0) slow[q] = 0;
+    uint64_t* cq = carry + static_cast<size_t>(q) * kpad;
+    for (int j = lane; j < kpad; j += 32) { sC[w][j] = cq[j]; sN[w][j] = 0ull; }
+    int off0 = incl - mine;
+#pragma unroll
+    for (int i = 0; i < kMwMaxPL; ++i) {
+        const int p = lane + 32 * i;
+        if (p < P) {
+            const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
+            for (int j = 0; j < cnt[i]; ++j) sS[w][off0 + j] = ld_cg_u64(e + j);
+            off0 += cnt[i];
+        }
+    }
+    __syncwarp();
+    // carry entries in use (sorted, zeros behind)
+    int c = 0;
+    for (int j0 = 0; j0 < kpad; j0 += 32) c += __popc(__ballot_sync(0xffffffffu, sC[w][j0 + lane] != 0ull));
+    // survivors best first: rank among themselves (composites are distinct)
+    for (int i = lane; i < m; i += 32) {
+        const uint64_t v = sS[w][i];
+        int r = 0;
+        for (int j = 0; j < m; ++j) r += (sS[w][j] > v) ? 1 : 0;
+        sT[w][r] = v;
+    }
+    __syncwarp();
+    // merged rank = own position + number of elements of the other sorted run that beat the element
+    for (int i = lane; i < m; i += 32) {
+        const uint64_t v = sT[w][i];
+        int lo = 0, hi = c;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sC[w][mid] > v) lo = mid + 1; else hi = mid; }
+        if (i + lo < k) sN[w][i + lo] = v;
+    }
+    for (int j = lane; j < c; j += 32) {
+        const uint64_t v = sC[w][j];
+        int lo = 0, hi = m;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sT[w][mid] > v) lo = mid + 1; else hi = mid; }
+        if (j + lo < k) sN[w][j + lo] = v;
+    }
+    __syncwarp();
+    for (int j = lane; j < kpad; j += 32) cq[j] = (j < k) ? sN[w][j] : 0ull;
+    if (lane == 0) tauc[q] = sN[w][k - 1];        // 0 while fewer than k rows have been seen
+#pragma unroll
+    for (int i = 0; i < kMwMaxPL; ++i) {
+        const int p = lane + 32 * i;
+        if (p < P) { counts[static_cast<size_t>(p) * Qp + q] = 0; lthr[static_cast<size_t>(p) * Qp + q] = 0ull; }
+    }
+    if (last && q < nq) {
+        for (int j = lane; j < k; j += 32) {
+            const uint64_t cv = sN[w][j];
+            float* so = out_scores + static_cast<size_t>(q) * k + j;
+            int64_t* io = out_idx + static_cast<size_t>(q) * k + j;
+            if (cv == 0) { *so = largest ? -INFINITY : INFINITY; *io = -1; }
+            else { *so = key_to_score(composite_key(cv), largest != 0); *io = static_cast<int64_t>(composite_idx(cv)) + idx_offset; }
+        }
+    }
+}
+
 __global__ void batch_init_kernel(uint64_t* carry, uint64_t* tauc, int* counts, uint64_t* lthr, size_t n_carry, size_t n_q, size_t n_pq) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n_carry) carry[i] = 0ull;
@@ -574,6 +670,7 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     const size_t o_b2 = take(static_cast<size_t>(Qp) * 4);
     const size_t o_qc = take(static_cast<size_t>(Qp) * 4);
     const size_t o_bq = take(static_cast<size_t>(Qp) * b->Dp * 2);
+    const size_t o_slow = take(static_cast<size_t>(Qp));
     int rc = ensure_ws(b, off);
     if (rc) return rc;
     unsigned char* ws = reinterpret_cast<unsigned char*>(b->ws);
@@ -586,6 +683,7 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     float* b2 = reinterpret_cast<float*>(ws + o_b2);
     float* qconst = reinterpret_cast<float*>(ws + o_qc);
     void* bq = ws + o_bq;
+    unsigned char* slow = ws + o_slow;
 
     rc = launch_pack_queries(t, Q, b->D, b->Dp, Qp, metric, bq, qconst, st);
     if (rc) return rc;
@@ -649,8 +747,16 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
             nsample = kMpSample;
         }
         const size_t msmem = static_cast<size_t>(kpad + pool + nsample) * 8;
+        const bool warp_merge = !first && kpad <= kMwMaxK && P <= 32 * kMwMaxPL;
+        if (warp_merge) {
+            merge_phase_warp_kernel<<<(Qp + kMwWarps - 1) / kMwWarps, kMwWarps * 32, 0, st>>>(
+                carry, tauc, lists, counts, lthr, slow, P, Qp, cap, k, kpad, metric_largest(metric) ? 1 : 0, last, Q, idx_offset,
+                out_scores, out_idx);
+            SKY_LAUNCH_CHECK("merge_phase_warp_kernel");
+        }
         merge_phase_kernel<<<Qp, kMpThreads, msmem, st>>>(carry, tauc, lists, counts, lthr, P, Qp, cap, k, kpad, pool, nsample,
-                                                         metric_largest(metric) ? 1 : 0, last, Q, idx_offset, out_scores, out_idx);
+                                                         metric_largest(metric) ? 1 : 0, last, Q, idx_offset, out_scores, out_idx,
+                                                         warp_merge ? slow : nullptr);
         SKY_LAUNCH_CHECK("merge_phase_kernel");
         t0 = t1;
         if (!first) per_cta *= growth;
