@@ -101,14 +101,18 @@ def test_cli_tile_mode_reads_fits_tiles(tmp_path):
         fitslite.write_image(str(tiles / f"calexp-HSC-{b}-9813-4,4.fits"), planes[i], hdr)
     coords = ingest.generate_overlap_coords((200, 200), 64, 0.4)
     h0, w0 = coords[5]
-    tgt = planes[None, :, h0:h0 + 64, w0:w0 + 64].copy()
+    # two slightly noisy copies of the cutout: a single un-augmented target has no spread, and the reference's weights
+    # 1 / std^2 (utils/similarity.py:143) are NaN then
+    rng = np.random.default_rng(0)
+    cut = planes[:, h0:h0 + 64, w0:w0 + 64]
+    tgt = (np.stack([cut, cut]) + 0.01 * rng.standard_normal((2, 5, 64, 64))).astype(np.float32)
     data = tmp_path / "data"
     data.mkdir()
-    h5lite.write_h5(str(data / "targets.h5"), dict(cutouts=tgt, ra=np.zeros(1, "f"), dec=np.zeros(1, "f")))
-    out = search.main(["stubmodel", "-tgt_fn", "targets.h5", "-tst_dirs", str(tiles), "-tgt_i", "[0]", "-aug", "False", "-mp", "True",
+    h5lite.write_h5(str(data / "targets.h5"), dict(cutouts=tgt, ra=np.zeros(2, "f"), dec=np.zeros(2, "f")))
+    out = search.main(["stubmodel", "-tgt_fn", "targets.h5", "-tst_dirs", str(tiles), "-tgt_i", "[0,1]", "-aug", "False", "-mp", "True",
                        "-bs", "4", "-ns", "5", "-dd", str(data), "--results-dir", str(tmp_path / "results"),
                        "--encoder", "tests.test_gpu_cli:stub_factory"])
     r = np.load(out)
     ra, dec = fitslite.TanWcs(hdr).all_pix2world([h0 + 32], [w0 + 32], 0)        # argument order as the reference calls it
     assert np.allclose(r["test_ra_decs"][0], [ra[0], dec[0]], atol=1e-4), "top hit is the cutout the target was cut from"
-    assert np.array_equal(r["test_images"][0], np.maximum(tgt[0], -3.0))
+    assert np.array_equal(r["test_images"][0], np.maximum(cut, -3.0))
