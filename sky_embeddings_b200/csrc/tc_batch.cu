@@ -43,9 +43,7 @@ struct TbParams {
     int Qp, nq, cap, k, groups, metric, kblocks;
     int64_t rows;              // valid bank rows
     int tile0, tile1;          // tiles [tile0, tile1) of this phase
-    int dense;                 // first phase, no bound exists yet.  1: every row is a candidate, lists are written densely;
-                               // 2: bootstrap pass -- only the best key of the tile per query is kept (gmax)
-    uint32_t* gmax;            // [P][Qp] dense == 2: best key of CTA p's tile for query q
+    int dense;                 // first phase: no bound exists, every row is a candidate -> lists are written densely
     int debug;                 // experiments: bit0 epilogue only drains TMEM, bit1 no MMA issue
     float inv_dd;
 };
@@ -245,27 +243,6 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             // one 32-column chunk: conservative pre-filter in the space of the accumulator (one FMA / ADD and one
             // compare per score, coefficients read with 128-bit shared loads issued up front), then the rare exact path
             auto process = [&](const uint32_t (&vv)[32], int c) {
-                if (p.dense == 2) {
-                    // BOOTSTRAP PASS (k <= number of CTAs): keep only the best key of this tile per query.  The k-th
-                    // largest of the CTAs' best keys is a valid lower bound of the global k-th best (each belongs to a
-                    // different bank row), so the first real phase already runs filtered -- instead of writing every
-                    // row of the first tiles into the lists (620 MB at 4096 queries) and merging 19 k candidates per query.
-                    const float4* pqc = reinterpret_cast<const float4*>(sQc + buf * kTbBN + c * 32);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 qv4 = pqc[i];
-                        const float qc4[4] = {qv4.x, qv4.y, qv4.z, qv4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float dot = __uint_as_float(vv[i * 4 + u]);
-                            const float sv = largest ? dot / fmaf(qc4[u], mx, 1e-6f) : (qc4[u] - 2.0f * dot + rn) * p.inv_dd;
-                            const uint32_t key = valid ? score_to_key(sv, largest) : 0u;
-                            const uint32_t best = __reduce_max_sync(0xffffffffu, key);
-                            if (lane == 0 && best) reds_max_u32(smem_addr(&sCnt[buf * kTbBN + c * 32 + i * 4 + u]), best);
-                        }
-                    }
-                    return;
-                }
                 if (p.dense) {
                     // FIRST PHASE: everything is a candidate.  No filter, no atomics: row r of the tile goes to slot r
                     // of the (empty) list of every query, 32 lanes = 256 contiguous bytes per store.
@@ -358,12 +335,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             TB_TRACE(4, inserted ? 1 : 0);
             // write the fills back; lists of this group that could not take another 128 rows are pruned in place
             // to their k best (rare once bounds exist), which also yields a CTA-local bound
-            if (p.dense == 2) {
-                ptx::named_bar_sync(2, kTbEpiThreads);               // all four warps have folded their maxima
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    p.gmax[static_cast<size_t>(blockIdx.x) * p.Qp + g * kTbBN + et + j * 128] = static_cast<uint32_t>(sCnt[buf * kTbBN + et + j * 128]);
-            } else if (p.dense) {
+            if (p.dense) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) st_cg_i32(my_counts + g * kTbBN + et + j * 128, kTileRows);
             } else if (!(SKY_DBG(p) & 8) && named_bar_or(3, kTbEpiThreads, inserted)) {
@@ -648,14 +620,6 @@ merge_phase_warp_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tau
     }
 }
 
-// After the bootstrap pass: tauc[q] = just below the k-th largest of the P per-CTA best keys (0 = fewer than k rows).
-__global__ void batch_boot_bounds_kernel(const uint32_t* __restrict__ gmax, int P, int Qp, int k, uint64_t* __restrict__ tauc) {
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= Qp) return;
-    const uint32_t kth = exchange_reduce(gmax + q, P, Qp, k);
-    if ((threadIdx.x & 31) == 0) tauc[q] = kth ? ((static_cast<uint64_t>(kth) << 32) - 1ull) : 0ull;
-}
-
 __global__ void batch_init_kernel(uint64_t* carry, uint64_t* tauc, int* counts, uint64_t* lthr, size_t n_carry, size_t n_q, size_t n_pq) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n_carry) carry[i] = 0ull;
@@ -707,7 +671,6 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     const size_t o_qc = take(static_cast<size_t>(Qp) * 4);
     const size_t o_bq = take(static_cast<size_t>(Qp) * b->Dp * 2);
     const size_t o_slow = take(static_cast<size_t>(Qp));
-    const size_t o_gmax = take(static_cast<size_t>(P) * Qp * 4);
     int rc = ensure_ws(b, off);
     if (rc) return rc;
     unsigned char* ws = reinterpret_cast<unsigned char*>(b->ws);
@@ -721,7 +684,6 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     float* qconst = reinterpret_cast<float*>(ws + o_qc);
     void* bq = ws + o_bq;
     unsigned char* slow = ws + o_slow;
-    uint32_t* gmax = reinterpret_cast<uint32_t*>(ws + o_gmax);
 
     rc = launch_pack_queries(t, Q, b->D, b->Dp, Qp, metric, bq, qconst, st);
     if (rc) return rc;
@@ -749,25 +711,10 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     p.inv_dd = 1.0f / (static_cast<float>(b->D) * static_cast<float>(b->D));
     const float dd = static_cast<float>(b->D) * static_cast<float>(b->D);
 
-    p.gmax = gmax;
-    // BOOTSTRAP instead of a dense first phase when k <= number of CTAs (see the kernel): one pass over the first P
-    // tiles that keeps the per-CTA best key per query, the k-th largest of those as the first bound, and the first
-    // real phase walks the same tiles filtered
-    bool first = true;
-    if (k <= P && num_tiles >= P && env_knob("SKY_TB_BOOT", 1) != 0) {
-        p.tile0 = 0; p.tile1 = P; p.dense = 2;
-        prof_mark(b, st);
-        if (metric == SKY_COSINE) tc_batch_kernel<true><<<P, kTbThreads, smem, st>>>(b->tmap_bank, tmq, p);
-        else tc_batch_kernel<false><<<P, kTbThreads, smem, st>>>(b->tmap_bank, tmq, p);
-        prof_mark(b, st);
-        SKY_LAUNCH_CHECK("tc_batch_kernel");
-        batch_boot_bounds_kernel<<<(Qp + 7) / 8, 256, 0, st>>>(gmax, P, Qp, k, tauc);
-        SKY_LAUNCH_CHECK("batch_boot_bounds_kernel");
-        first = false;
-    }
     // phases: 1, 1, 2, 4, ... tiles per CTA
     int t0 = 0;
     int per_cta = 1;
+    bool first = true;
     int growth = 4;       // phase sizes 1, 1, 4, 16, ... tiles per CTA (measured: growth 16 saves two merges on a small shard but its
                           // k ln 17 survivors per query overflow lists and pools at k = 1000: C4's share 20 -> 29 ms)
     { const int e = env_knob("SKY_TB_PHASE0", 0); if (e >= 1) per_cta = e; }
