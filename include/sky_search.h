@@ -116,7 +116,12 @@ SKY_API int sky_query_from_targets(const sky_bank_t* bank, const float* targets,
  *  t[Q,D], w[Q,D] f32 (w NULL = ones, i.e. use_weights=False); n_top_sims 0 = None (:257-259).
  *  out_scores[Q,k] f32 best-first, out_idx[Q,k] i64 bank item index (+ idx_offset);
  *  when the bank has fewer than k items the tail is padded like the reference's initial fill
- *  (:66: -inf for cosine, +inf otherwise) with index -1.  NaN scores rank as the largest value. */
+ *  (:66: -inf for cosine, +inf otherwise) with index -1.  NaN scores rank as the largest value.
+ *  Precision: SKY_PATH_SIMT / GENERIC keep the queries in fp32 (fp32 bank: 1e-5 relative to the reference).  The tensor
+ *  paths (TENSOR / BATCH; AUTO picks them only for Q > 4 on a bf16 bank) round the query operands to bf16 (t; with
+ *  weights w*t and w) and derive the per-query constants from the rounded operands, so scores are true cosines /
+ *  squared distances of the rounded vectors: within ~1e-3 of a typical score of the bank (measured bounds: DESIGN.md
+ *  section 5).  One search at a time per bank handle: the candidate state lives in the handle's scratch. */
 SKY_API int sky_search(sky_bank_t* bank, const float* t, const float* w, int Q, int metric, int combine,
                int n_top_sims, int k, int64_t idx_offset, float* out_scores, int64_t* out_idx,
                int path, void* stream);
