@@ -21,6 +21,3 @@ try:
 except Exception as e:
     print('summary failed', e)
 PY
-timeout 300 python scripts/measure_bf16_bounds.py > gpurun_out/bf16_bounds.txt 2>&1; echo "bounds rc=$?"; cat gpurun_out/bf16_bounds.txt | tail -5
-SKY_NVCC_DEFS=-DSKY_EXPERIMENTS python -m sky_embeddings_b200.build --force > gpurun_out/build_exp.log 2>&1; echo "build rc=$?"
-for v in 0 1 0 1; do SKY_TC_TMA=$v timeout 120 python scripts/time_search.py --tag k2_tma$v | tail -1; done
