@@ -113,4 +113,23 @@ void count_launch(int n = 1);
                                     cudaGetErrorString(_e));                                  \
     } while (0)
 
+// Launch `kernel` so that it may start while the previous kernel of the stream drains (see ptx::griddep_wait: the
+// kernel MUST call it before touching anything its predecessor wrote).  pdl = false: an ordinary launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_maybe_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+constexpr int kUsePdl = 1;      // experiments: SKY_PDL=0 launches everything the ordinary way
+
 }  // namespace sky

@@ -7,6 +7,7 @@
 // Output padding when fewer than k candidates exist follows the reference's initial fill
 // (utils/similarity.py:66): -inf for cosine, +inf otherwise; index -1.
 #include "bank.cuh"
+#include "ptx.cuh"
 #include "topk.cuh"
 
 namespace sky {
@@ -48,6 +49,7 @@ merge_lists_kernel(const uint64_t* __restrict__ lists, const int* __restrict__ c
     constexpr int nwarps = kMergeThreads / 32;
 
     if (tid == 0) { npool = 0; tau_s = 0u; }
+    ptx::griddep_wait();      // launched with programmatic serialization: the scorer's lists are complete from here on
     __syncthreads();
     // list fills: issued before the bound reduction so both L2 round trips overlap
     constexpr int kCountCache = 2048;
@@ -241,9 +243,9 @@ int launch_merge_lists(const SearchState& s, int metric, int64_t idx_offset, flo
     const int kpad = next_pow2(s.k);
     const size_t smem = static_cast<size_t>(kpad + kPool) * sizeof(uint64_t);
     SKY_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    merge_lists_kernel<<<s.Qtot, kMergeThreads, smem, st>>>(s.lists, s.counts, s.gtop, s.P, s.p_stride, s.Qtot, s.cap,
-                                                           s.k, kpad, s.use_gtau, metric_largest(metric) ? 1 : 0,
-                                                           idx_offset, out_scores, out_idx, xt ? *xt : XchgTarget{});
+    SKY_CUDA(launch_maybe_pdl(env_knob("SKY_PDL", kUsePdl) != 0, merge_lists_kernel, dim3(s.Qtot), dim3(kMergeThreads), smem, st,
+                              s.lists, s.counts, s.gtop, s.P, s.p_stride, s.Qtot, s.cap, s.k, kpad, s.use_gtau,
+                              metric_largest(metric) ? 1 : 0, idx_offset, out_scores, out_idx, xt ? *xt : XchgTarget{}));
     SKY_LAUNCH_CHECK("merge_lists_kernel");
     if (xt) xt->fused = true;
     return SKY_OK;

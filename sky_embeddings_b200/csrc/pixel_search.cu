@@ -155,12 +155,15 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
         for (int g = 0; g < my_groups; ++g) {
             const int64_t r0 = p.row_lo + (blockIdx.x + static_cast<int64_t>(g) * gridDim.x) * kPxRows;
             const int rows = static_cast<int>(p.row_hi - r0 < kPxRows ? p.row_hi - r0 : kPxRows);
+            // the pixel counts are kept as floats (exact: a row has 20480 < 2^24 pixels): a predicated FADD on the
+            // fp32 pipe next to the predicated FFMA, where an integer count costs two ALU-pipe instructions per
+            // pixel and query (add + select) and made the general path ALU-bound at 4 queries per pass
             float acc[kPxRows][QC];
-            int cnt[kPxRows][QC];
+            float cnt[kPxRows][QC];
 #pragma unroll
             for (int r = 0; r < kPxRows; ++r)
 #pragma unroll
-                for (int q = 0; q < QC; ++q) { acc[r][q] = 0.f; cnt[r][q] = 0; }
+                for (int q = 0; q < QC; ++q) { acc[r][q] = 0.f; cnt[r][q] = 0.f; }
 
             for (int c = 0; c < p.nch; ++c) {
                 const int len = (c == p.nch - 1) ? last_len : kPxChunkElems;
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
                                 const bool in = e0 + j * 128 < len;      // a short last piece: stale ring data beyond it
                                 const bool p0 = in && xv[j].x == xv[j].x, p1 = in && xv[j].y == xv[j].y;
                                 const bool p2 = in && xv[j].z == xv[j].z, p3 = in && xv[j].w == xv[j].w;
-                                cnt[r][0] += (p0 ? 1 : 0) + (p1 ? 1 : 0) + (p2 ? 1 : 0) + (p3 ? 1 : 0);
+                                cnt[r][0] += static_cast<float>((p0 ? 1 : 0) + (p1 ? 1 : 0) + (p2 ? 1 : 0) + (p3 ? 1 : 0));
 #pragma unroll
                                 for (int q = 0; q < QC; ++q) {
                                     const float d0 = qv[q][j].x - xv[j].x, d1 = qv[q][j].y - xv[j].y;
@@ -217,10 +220,10 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
                                     const float d0 = qv[q][j].x - xv[j].x, d1 = qv[q][j].y - xv[j].y;
                                     const float d2 = qv[q][j].z - xv[j].z, d3 = qv[q][j].w - xv[j].w;
                                     // NaN (either side missing or masked out) drops out of both sums
-                                    if (d0 == d0) { acc[r][q] = fmaf(d0, d0, acc[r][q]); cnt[r][q] += 1; }
-                                    if (d1 == d1) { acc[r][q] = fmaf(d1, d1, acc[r][q]); cnt[r][q] += 1; }
-                                    if (d2 == d2) { acc[r][q] = fmaf(d2, d2, acc[r][q]); cnt[r][q] += 1; }
-                                    if (d3 == d3) { acc[r][q] = fmaf(d3, d3, acc[r][q]); cnt[r][q] += 1; }
+                                    if (d0 == d0) { acc[r][q] = fmaf(d0, d0, acc[r][q]); cnt[r][q] += 1.f; }
+                                    if (d1 == d1) { acc[r][q] = fmaf(d1, d1, acc[r][q]); cnt[r][q] += 1.f; }
+                                    if (d2 == d2) { acc[r][q] = fmaf(d2, d2, acc[r][q]); cnt[r][q] += 1.f; }
+                                    if (d3 == d3) { acc[r][q] = fmaf(d3, d3, acc[r][q]); cnt[r][q] += 1.f; }
                                 }
                         }
                         __syncwarp();
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
 #pragma unroll
                 for (int q = 0; q < QC; ++q) {
                     float a = acc[r][q];
-                    int n = clean ? cnt[r][0] : cnt[r][q];
+                    float n = clean ? cnt[r][0] : cnt[r][q];
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) {
                         a += __shfl_xor_sync(0xffffffffu, a, off);
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
                     }
                     if (lane == 0) {
                         sPart[((warp * kPxRows + r) * QC + q) * 2] = a;
-                        sPart[((warp * kPxRows + r) * QC + q) * 2 + 1] = static_cast<float>(n);
+                        sPart[((warp * kPxRows + r) * QC + q) * 2 + 1] = n;
                     }
                 }
             ptx::named_bar_sync(1, kPxConsumers);

@@ -139,6 +139,10 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
     volatile int* sBlocksDone = reinterpret_cast<volatile int*>(sHist + kStWarps * 256);   // [1]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Programmatic dependent launch (search mode): this grid may start while the kernel that zeroes the exchange state
+    // (init_state_kernel) still runs.  The query staging, the bank stream and the scoring do not depend on it; the two
+    // places that touch the exchange state (exchange warp, final publish + counts) wait for it first.
+    ptx::griddep_launch_dependents();
 
     // row blocks of this CTA: rb_lo + blockIdx.x, + gridDim.x, ...
     const int64_t rb_lo = p.row_lo / R, rb_hi = (p.row_hi + R - 1) / R;
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
     } else if (warp == kStXchgWarp) {
         // ===================== grid-wide bound exchange =====================
         if (!emit && p.use_gtau && my_blocks > 0) {
+            ptx::griddep_wait();
             uint32_t* my_row = p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0;
             int round = 0;
             uint32_t published = 0;      // lane q: the key this CTA last published for query q
@@ -483,6 +488,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_search_kernel(const Stre
             if (tid == 0) *sBlocksDone = i + 1;
         }
         if (!emit) {
+            ptx::griddep_wait();
             ptx::named_bar_sync(1, kStConsumers);
             if (tid < p.nq && p.use_gtau && sLmax[tid])
                 st_cg_u32(p.gtop + static_cast<size_t>(blockIdx.x) * p.Qtot + p.q0 + tid, sLmax[tid]);
@@ -553,7 +559,10 @@ template <typename BankT, int METRIC, int QC, bool WEIGHTED>
 static int stream_launch_one(const StreamParams& p, int grid, size_t smem, cudaStream_t st) {
     SKY_CUDA(cudaFuncSetAttribute(stream_search_kernel<BankT, METRIC, QC, WEIGHTED>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    stream_search_kernel<BankT, METRIC, QC, WEIGHTED><<<grid, kStThreads, smem, st>>>(p);
+    // search mode follows init_state_kernel (or the previous pass of this kernel): start under its tail.  Emit mode
+    // (sky_score) may follow the caller's own kernels, which can have produced the query: ordinary launch.
+    const bool pdl = p.emit == nullptr && env_knob("SKY_PDL", kUsePdl) != 0;
+    SKY_CUDA(launch_maybe_pdl(pdl, stream_search_kernel<BankT, METRIC, QC, WEIGHTED>, dim3(grid), dim3(kStThreads), smem, st, p));
     SKY_LAUNCH_CHECK("stream_search_kernel");
     return SKY_OK;
 }

@@ -30,6 +30,7 @@ constexpr int kTbStageA = kTileRows * 128;     // 16 KB: 128 rows x 64 bf16
 constexpr int kTbStageB = kTbBN * 128;         // 32 KB: 256 queries x 64 bf16
 constexpr int kTbStage = kTbStageA + kTbStageB;
 constexpr int kTbStages = 4;
+constexpr int kTbSmallK = 256;                 // k up to which the dense first phase is cut short (launch_tc_batch)
 
 struct TbParams {
     const float* rownorm;      // [rows_pad]
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(kMpThreads)
 merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, const uint64_t* __restrict__ lists,
                    int* __restrict__ counts, uint64_t* __restrict__ lthr, int P, int Qp, int cap, int k, int kpad, int kMpPool, int nsample, int largest,
                    int last, int nq, int64_t idx_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
-                   const unsigned char* __restrict__ only) {
+                   const unsigned char* __restrict__ only, int keep_sorted) {
     if (only && !only[blockIdx.x]) return;        // this query was merged by the warp-per-query kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);    // [kpad]
@@ -461,11 +462,17 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
     }
     __syncthreads();
     bool done = false;
+    // the carry between two phases only has to be the right SET (this kernel gathers it into the pool again); sorted
+    // order is needed by the last phase (the result) and by the warp-per-query merge (binary searches over the carry)
+    const bool sorted = last || keep_sorted;
+    uint64_t kth = 0;
+    bool have_kth = false;
     if (np <= kRankSortMax) {
         block_rank_topk(pool, np, k, kpad, sel);
         done = true;
     } else if (np <= kMpPool) {
-        block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch);
+        kth = block_select_sort([&](int j) { return pool[j]; }, np, k, kpad, sel, hist, scratch, sorted);
+        have_kth = true;
         done = true;
     } else {
         // big candidate set (first phase: every row of every CTA): the k-th best of the sample is a lower bound of
@@ -513,7 +520,7 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
     }
     __syncthreads();
     for (int j = tid; j < kpad; j += kMpThreads) cq[j] = (j < k) ? sel[j] : 0ull;
-    if (tid == 0) tauc[q] = sel[k - 1];        // 0 while fewer than k rows have been seen
+    if (tid == 0) tauc[q] = have_kth ? kth : sel[k - 1];        // 0 while fewer than k rows have been seen
     for (int p = tid; p < P; p += kMpThreads) { counts[static_cast<size_t>(p) * Qp + q] = 0; lthr[static_cast<size_t>(p) * Qp + q] = 0ull; }
     if (last && q < nq) {
         for (int j = tid; j < k; j += kMpThreads) {
@@ -719,8 +726,19 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
                           // k ln 17 survivors per query overflow lists and pools at k = 1000: C4's share 20 -> 29 ms)
     { const int e = env_knob("SKY_TB_PHASE0", 0); if (e >= 1) per_cta = e; }
     { const int e = env_knob("SKY_TB_GROWTH", 0); if (e >= 2) growth = e; }
+    // Dense first phase: its only job is a first bound, and every row it takes is a candidate the first merge must read
+    // (P tiles = 18 944 rows per query; on a small shard that merge was the largest single item after the scoring itself).
+    // For small k a few dozen tiles already give a bound that rejects all but k / rows of the next phase, and their
+    // rows + the carry fit the merge's pool in one pass: take (4096 - k) / 128 tiles when the bank is long enough for the
+    // idle SMs of that short launch not to matter.
+    int dense_tiles = P;
+    if (k <= kTbSmallK && num_tiles >= 4 * P) {
+        const int t = (4096 - k) / kTileRows;
+        if (t < dense_tiles) dense_tiles = t;
+    }
+    { const int e = env_knob("SKY_TB_DENSE0", 0); if (e >= 1) dense_tiles = e < P ? e : P; }
     while (t0 < num_tiles) {
-        int t1 = t0 + per_cta * P;
+        int t1 = t0 + ((first && per_cta == 1) ? dense_tiles : per_cta * P);
         if (t1 > num_tiles || num_tiles - t1 < P) t1 = num_tiles;      // fold a short tail into this phase
         batch_bounds_kernel<<<(Qp + 255) / 256, 256, 0, st>>>(tauc, qconst, Q, Qp, metric, dd, b1, b2);
         SKY_LAUNCH_CHECK("batch_bounds_kernel");
@@ -756,7 +774,7 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
         }
         merge_phase_kernel<<<Qp, kMpThreads, msmem, st>>>(carry, tauc, lists, counts, lthr, P, Qp, cap, k, kpad, pool, nsample,
                                                          metric_largest(metric) ? 1 : 0, last, Q, idx_offset, out_scores, out_idx,
-                                                         warp_merge ? slow : nullptr);
+                                                         warp_merge ? slow : nullptr, (kpad <= kMwMaxK || env_knob("SKY_TB_SORTED", 0)) ? 1 : 0);
         SKY_LAUNCH_CHECK("merge_phase_kernel");
         t0 = t1;
         if (!first) per_cta *= growth;

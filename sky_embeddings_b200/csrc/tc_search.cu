@@ -126,6 +126,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         ptx::tmem_alloc(sTmemBase, 2 * BN);
         ptx::tmem_relinquish();
     }
+    // everything above overlaps the tail of the packing kernel (programmatic dependent launch); from here on the
+    // kernel reads what that kernel wrote: query constants, the bf16 query matrix, the zeroed exchange state
+    ptx::griddep_wait();
+    ptx::griddep_launch_dependents();      // the merge kernel may be scheduled as soon as SMs free up
     for (int q = tid; q < BN; q += kTcThreads) {
         sThr[q] = (q < p.nq) ? 0ull : ~0ull;
         // NaN lets everything through the pre-filter; padding queries are rejected by it
@@ -436,6 +440,7 @@ int debug_read_epi(unsigned long long* h_out) {
 // Queries -> bf16 operand matrix [q_pad, Dp] (zero padded) + per-query constants.
 __global__ void pack_queries_kernel(const float* __restrict__ t, int Q, int D, int Dp, int q_pad, int metric,
                                     __nv_bfloat16* __restrict__ bq, float* __restrict__ qconst, const StateInit si) {
+    ptx::griddep_launch_dependents();      // the scorer behind this kernel may set itself up now (it waits before reading)
     state_init_gridwide(si);
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -581,7 +586,8 @@ int launch_tc_search(sky_bank* b, const float* t, int Q, int metric, const Searc
         p.inv_dd = 1.0f / (static_cast<float>(b->D) * static_cast<float>(b->D));
         prof_mark(b, st);
         p.use_tma = (b->tmap_ready && env_knob("SKY_TC_TMA", kTcUseTma) != 0) ? 1 : 0;
-        tc_search_kernel<BN><<<grid, kTcThreads, smem, st>>>(tmq, b->tmap_bank, p);
+        SKY_CUDA(launch_maybe_pdl(env_knob("SKY_PDL", kUsePdl) != 0, tc_search_kernel<BN>, dim3(grid), dim3(kTcThreads), smem, st,
+                                  tmq, b->tmap_bank, p));
         prof_mark(b, st);
         SKY_LAUNCH_CHECK("tc_search_kernel");
     }

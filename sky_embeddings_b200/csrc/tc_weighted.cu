@@ -465,6 +465,10 @@ tc_weighted2_kernel(const __grid_constant__ CUtensorMap tmap_bank, const __grid_
         ptx::tmem_alloc2(sTmemBase, 512);           // 2 x (D1 | D2) accumulators + S squared k-blocks, in both CTAs
         ptx::tmem_relinquish2();
     }
+    // programmatic dependent launch: the set-up above ran under the tail of the packing kernel; its outputs (query
+    // constants, operand matrices, zeroed exchange state) are read from here on
+    ptx::griddep_wait();
+    ptx::griddep_launch_dependents();
     for (int q = tid; q < kTwBN; q += kT2Threads) {
         sThr[q] = (q < p.nq) ? 0ull : ~0ull;
         sThrF[q] = (q < p.nq) ? __uint_as_float(0x7FC00000u) : (largest ? INFINITY : -INFINITY);
@@ -734,6 +738,7 @@ int debug_read_tw_trace(unsigned long long* h_out, int n) {
 __global__ void pack_weighted_kernel(const float* __restrict__ t, const float* __restrict__ w, int nq, int D, int Dp, int metric,
                                      __nv_bfloat16* __restrict__ ba, __nv_bfloat16* __restrict__ bw,
                                      float* __restrict__ qc1, float* __restrict__ qc2, const StateInit si) {
+    ptx::griddep_launch_dependents();      // the scorer behind this kernel may set itself up now (it waits before reading)
     state_init_gridwide(si);
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -861,8 +866,9 @@ int launch_tc_weighted(sky_bank* b, const float* t, const float* w, int Q, int m
                 cudaOccupancyMaxActiveClusters(&ncl, tc_weighted2_kernel<true>, &cfg);
                 fprintf(stderr, "[sky] K2w2 grid %d, smem %zu, stages %d, max active clusters %d\n", s.P, smem, pp.stages, ncl);
             }
-            if (metric == SKY_COSINE) tc_weighted2_kernel<true><<<s.P, kT2Threads, smem, st>>>(b->tmap_bank, tma, tmw, pp);
-            else tc_weighted2_kernel<false><<<s.P, kT2Threads, smem, st>>>(b->tmap_bank, tma, tmw, pp);
+            const bool pdl = env_knob("SKY_PDL", kUsePdl) != 0;
+            if (metric == SKY_COSINE) SKY_CUDA(launch_maybe_pdl(pdl, tc_weighted2_kernel<true>, dim3(s.P), dim3(kT2Threads), smem, st, b->tmap_bank, tma, tmw, pp));
+            else SKY_CUDA(launch_maybe_pdl(pdl, tc_weighted2_kernel<false>, dim3(s.P), dim3(kT2Threads), smem, st, b->tmap_bank, tma, tmw, pp));
         } else if (metric == SKY_COSINE) tc_weighted_kernel<true><<<s.P, kTwThreads, smem, st>>>(tma, tmw, p);
         else tc_weighted_kernel<false><<<s.P, kTwThreads, smem, st>>>(tma, tmw, p);
         prof_mark(b, st);

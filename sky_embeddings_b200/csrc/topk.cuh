@@ -318,10 +318,13 @@ __device__ __forceinline__ void state_init_gridwide(const StateInit& si) {
 // Radix-selects the k-th largest, gathers the winners into sel[kpad] (smem, kpad = pow2 >= k),
 // bitonic-sorts them descending.  Afterwards sel[0..k) holds the result (0 = padding).
 //   hist: 256 u32 smem; scratch: 4 u32 smem.
+// sorted = false: a caller that only needs the SET of winners and the k-th best (a running top-k between two phases)
+// skips the bitonic sort -- more than half of the barriers of this routine at kpad = 1024 -- whenever more than k
+// candidates exist; the return value is the k-th best composite (0 while fewer than k candidates exist).
 // ---------------------------------------------------------------------------------------------
 template <typename Fetch>
-__device__ void block_select_sort(Fetch fetch, int n, int k, int kpad, uint64_t* sel, uint32_t* hist,
-                                  uint32_t* scratch) {
+__device__ uint64_t block_select_sort(Fetch fetch, int n, int k, int kpad, uint64_t* sel, uint32_t* hist,
+                                      uint32_t* scratch, bool sorted = true) {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) { scratch[0] = 0; scratch[3] = 0; }
     __syncthreads();
@@ -368,6 +371,7 @@ __device__ void block_select_sort(Fetch fetch, int n, int k, int kpad, uint64_t*
         }
     }
     __syncthreads();
+    if (!sorted && total > k) return thr;      // sel[0..k) = the k winners in arbitrary order (composites are distinct)
     // bitonic sort, descending
     for (int size = 2; size <= kpad; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -381,6 +385,7 @@ __device__ void block_select_sort(Fetch fetch, int n, int k, int kpad, uint64_t*
             __syncthreads();
         }
     }
+    return sel[k - 1];
 }
 
 // ---------------------------------------------------------------------------------------------
