@@ -17,6 +17,11 @@ CASES = {
               {"SKY_TB_DENSE0": "16"}, {"SKY_TB_DENSE0": "62"}]),
     "c4g8": (12_500_000, 1000, 1000, "cosine", False, "bf16", "batch", 4,
              [{"SKY_TB_SORTED": "1"}, {}, {"SKY_TB_GROWTH": "8"}, {"SKY_TB_GROWTH": "6"}]),
+    # release-library runs (knobs are ignored there): the same setting twice shows the run-to-run noise
+    "c3g8r": (1_250_000, 4096, 100, "MSE", False, "bf16", "batch", 20, [{}, {}]),
+    "c4g8r": (12_500_000, 1000, 1000, "cosine", False, "bf16", "batch", 6, [{}, {}]),
+    "c3r": (10_000_000, 4096, 100, "MSE", False, "bf16", "batch", 4, [{}, {}]),
+    "c2r": (1_000_000, 64, 100, "cosine", False, "bf16", "auto", 300, [{}, {}]),
     "c3": (10_000_000, 4096, 100, "MSE", False, "bf16", "batch", 3,
            [{"SKY_TB_DENSE0": "148"}, {}, {"SKY_TB_GROWTH": "8"}]),
 }

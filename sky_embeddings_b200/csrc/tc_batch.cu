@@ -30,7 +30,7 @@ constexpr int kTbStageA = kTileRows * 128;     // 16 KB: 128 rows x 64 bf16
 constexpr int kTbStageB = kTbBN * 128;         // 32 KB: 256 queries x 64 bf16
 constexpr int kTbStage = kTbStageA + kTbStageB;
 constexpr int kTbStages = 4;
-constexpr int kTbSmallK = 256;                 // k up to which the dense first phase is cut short (launch_tc_batch)
+constexpr int kTbQueue = 512;                  // survivor queue entries per epilogue warp (4 x 4 KB of shared memory)
 
 struct TbParams {
     const float* rownorm;      // [rows_pad]
@@ -100,7 +100,8 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     float* sQc = sB2 + 2 * kTbBN;                                                   // [2][256] |t| or |t|^2
     int* sCnt = reinterpret_cast<int*>(sQc + 2 * kTbBN);                            // [2][256] list fill of this CTA
     uint32_t* sHist = reinterpret_cast<uint32_t*>(sCnt + 2 * kTbBN);                // [4][256]
-    uint32_t* sTmemBase = sHist + 4 * 256;
+    uint2* sQueue = reinterpret_cast<uint2*>(sHist + 4 * 256);                      // [4][kTbQueue] survivors of a visit
+    uint32_t* sTmemBase = reinterpret_cast<uint32_t*>(sQueue + 4 * kTbQueue);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr bool largest = COS;
@@ -212,6 +213,9 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
         };
         prefetch_group(0);
+        uint2* myq = sQueue + e * kTbQueue;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        int qn = 0;                               // queue fill (warp-uniform); empty at the end of every visit
 
         for (int v = 0; v < visits; ++v) {
             const int it = v / G, g = v - it * G;
@@ -241,6 +245,36 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTbBN);
             bool inserted = false;
+            // DRAIN the survivor queue, 32 entries per step, one per lane: exact score, composite, test against the
+            // query's bound, append to the CTA's list.  The dependent chain of a survivor (shared loads, division, shared
+            // atomic, global store: ~350 cycles) used to run once per survivor on the warp that found it, with nothing
+            // to overlap -- 43 ns of epilogue per survivor and CTA, 4.8 of C4's 17.4 ms per GPU (k = 1000 lets ~16 k rows
+            // per query through); here it runs for 32 survivors at a time.  Row terms come from the lane that owns the row.
+            auto drain = [&]() {
+                __syncwarp();
+                for (int i0 = 0; i0 < qn; i0 += 32) {
+                    const bool has = i0 + lane < qn;
+                    const uint2 en = has ? myq[i0 + lane] : make_uint2(0u, static_cast<uint32_t>(lane) << 8);
+                    const int sl = static_cast<int>(en.y >> 8) & 31, col = static_cast<int>(en.y & 255u);
+                    const float rn_s = __shfl_sync(0xffffffffu, rn, sl);
+                    if (has) {
+                        const float dot = __uint_as_float(en.x);
+                        const int qi = buf * kTbBN + col;
+                        const float qcv = sQc[qi];
+                        const float sv = largest ? dot / fmaf(qcv, sqrtf(rn_s), 1e-6f) : (qcv - 2.0f * dot + rn_s) * p.inv_dd;
+                        const uint32_t row_s = static_cast<uint32_t>(static_cast<int64_t>(tile) * kTileRows + quarter * 32 + sl);
+                        const uint64_t comp = make_composite(score_to_key(sv, largest), row_s);
+                        if (comp > sTau[qi] && !(SKY_DBG(p) & 16)) {
+                            // cap >= k + 256 and at most 128 rows per visit: the list cannot overflow before the check below
+                            const uint32_t pos = atoms_add_u32(smem_addr(&sCnt[qi]), 1u);
+                            st_cg_u64(my_lists + static_cast<size_t>(g * kTbBN + col) * p.cap + pos, comp);
+                            inserted = true;
+                        }
+                    }
+                }
+                __syncwarp();
+                qn = 0;
+            };
             // one 32-column chunk: conservative pre-filter in the space of the accumulator (one FMA / ADD and one
             // compare per score, coefficients read with 128-bit shared loads issued up front), then the rare exact path
             auto process = [&](const uint32_t (&vv)[32], int c) {
@@ -284,34 +318,32 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
                 if (SKY_DBG(p) & 4) mbits = 0;
                 mbits = valid ? mbits : 0u;
-                // EXACT PATH (rare once bounds exist): every lane walks its own survivors -- the warp runs as many
-                // rounds as its busiest lane has bits; columns beyond the real queries carry a +inf bound and never pass
+                // SURVIVORS go to this warp's queue as (accumulator bits, column, lane); the exact test and the insert
+                // happen in drain().  Every lane takes its lowest set bit per round (the warp runs as many rounds as its
+                // busiest lane has bits); a round is ballot + select tree + one shared store, nothing to wait for.
+                // columns beyond the real queries carry a +inf bound and never pass
 #pragma unroll 1
-                while (mbits) {
-                    const int j = __ffs(mbits) - 1;
-                    mbits &= mbits - 1;
-                    // vv[j] by a 5-level select tree (depth 5 instead of a 32-deep chain)
-                    uint32_t s16[16], s8[8], s4[4], s2[2];
+                for (;;) {
+                    const uint32_t act = __ballot_sync(0xffffffffu, mbits != 0u);
+                    if (act == 0u) break;
+                    if (qn > kTbQueue - 32) drain();
+                    if (mbits) {
+                        const int j = __ffs(mbits) - 1;
+                        mbits &= mbits - 1;
+                        // vv[j] by a 5-level select tree (depth 5 instead of a 32-deep chain)
+                        uint32_t s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) s16[i] = (j & 1) ? vv[2 * i + 1] : vv[2 * i];
+                        for (int i = 0; i < 16; ++i) s16[i] = (j & 1) ? vv[2 * i + 1] : vv[2 * i];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) s8[i] = (j & 2) ? s16[2 * i + 1] : s16[2 * i];
+                        for (int i = 0; i < 8; ++i) s8[i] = (j & 2) ? s16[2 * i + 1] : s16[2 * i];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) s4[i] = (j & 4) ? s8[2 * i + 1] : s8[2 * i];
+                        for (int i = 0; i < 4; ++i) s4[i] = (j & 4) ? s8[2 * i + 1] : s8[2 * i];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) s2[i] = (j & 8) ? s4[2 * i + 1] : s4[2 * i];
-                    const float dot = __uint_as_float((j & 16) ? s2[1] : s2[0]);
-                    const int q = g * kTbBN + c * 32 + j;
-                    const int qi = buf * kTbBN + c * 32 + j;
-                    const float qcv = sQc[qi];
-                    const float sv = largest ? dot / fmaf(qcv, mx, 1e-6f) : (qcv - 2.0f * dot + rn) * p.inv_dd;
-                    const uint64_t comp = make_composite(score_to_key(sv, largest), static_cast<uint32_t>(row));
-                    if (comp > sTau[qi] && !(SKY_DBG(p) & 16)) {
-                        // cap >= k + 256 and at most 128 rows per visit: the list cannot overflow before the check below
-                        const uint32_t pos = atoms_add_u32(smem_addr(&sCnt[qi]), 1u);
-                        st_cg_u64(my_lists + static_cast<size_t>(q) * p.cap + pos, comp);
-                        inserted = true;
+                        for (int i = 0; i < 2; ++i) s2[i] = (j & 8) ? s4[2 * i + 1] : s4[2 * i];
+                        const uint32_t dotbits = (j & 16) ? s2[1] : s2[0];
+                        myq[qn + __popc(act & lt_mask)] = make_uint2(dotbits, static_cast<uint32_t>(c * 32 + j) | (static_cast<uint32_t>(lane) << 8));
                     }
+                    qn += __popc(act);
                 }
             };
             // software pipeline over the 8 chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c is filtered
@@ -332,6 +364,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
                 if (!(SKY_DBG(p) & 1)) process(vb, 2 * c2 + 1);
             }
+            if (!p.dense) drain();
             TB_TRACE(2, clock64());
             TB_TRACE(4, inserted ? 1 : 0);
             // write the fills back; lists of this group that could not take another 128 rows are pruned in place
@@ -704,7 +737,7 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     rc = make_tmap_2d(&tmq, bq, Qp, b->Dp, kTbBN);
     if (rc) return rc;
 
-    const size_t smem = 1024 + static_cast<size_t>(kTbStages) * kTbStage + (2 * kTbStages + 4) * 8 + 2 * kTbBN * 8 + 8 * kTbBN * 4 + 4 * 256 * 4 + 64;
+    const size_t smem = 1024 + static_cast<size_t>(kTbStages) * kTbStage + (2 * kTbStages + 4) * 8 + 2 * kTbBN * 8 + 8 * kTbBN * 4 + 4 * 256 * 4 + 4 * kTbQueue * 8 + 64;
     SKY_CUDA(cudaFuncSetAttribute(tc_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SKY_CUDA(cudaFuncSetAttribute(tc_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SKY_CUDA(cudaFuncSetAttribute(merge_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -726,16 +759,10 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
                           // k ln 17 survivors per query overflow lists and pools at k = 1000: C4's share 20 -> 29 ms)
     { const int e = env_knob("SKY_TB_PHASE0", 0); if (e >= 1) per_cta = e; }
     { const int e = env_knob("SKY_TB_GROWTH", 0); if (e >= 2) growth = e; }
-    // Dense first phase: its only job is a first bound, and every row it takes is a candidate the first merge must read
-    // (P tiles = 18 944 rows per query; on a small shard that merge was the largest single item after the scoring itself).
-    // For small k a few dozen tiles already give a bound that rejects all but k / rows of the next phase, and their
-    // rows + the carry fit the merge's pool in one pass: take (4096 - k) / 128 tiles when the bank is long enough for the
-    // idle SMs of that short launch not to matter.
+    // Dense first phase = one tile per CTA.  Measured on C3's 8-GPU shard (1.25 M rows, Q = 4096, k = 100): cutting it to
+    // 31 tiles (so that the first merge reads 4 k instead of 19 k candidates per query) LOSES 0.7 ms -- the weaker first
+    // bound lets 4.8 k instead of 1 k rows per query through the next phase, and survivors are what costs (see the queue).
     int dense_tiles = P;
-    if (k <= kTbSmallK && num_tiles >= 4 * P) {
-        const int t = (4096 - k) / kTileRows;
-        if (t < dense_tiles) dense_tiles = t;
-    }
     { const int e = env_knob("SKY_TB_DENSE0", 0); if (e >= 1) dense_tiles = e < P ? e : P; }
     while (t0 < num_tiles) {
         int t1 = t0 + ((first && per_cta == 1) ? dense_tiles : per_cta * P);

@@ -27,3 +27,17 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_refuses_every_experiment_knob_the_library_reads():
+    """bench.py refuses to print a bench line while an experiment knob is set; its list must name every
+    env_knob("SKY_...") the sources read (they are only compiled in with -DSKY_EXPERIMENTS)."""
+    import glob
+    import re
+    sys.path.insert(0, ROOT)
+    import bench
+    names = set()
+    for f in glob.glob(os.path.join(ROOT, "sky_embeddings_b200", "csrc", "*.cu*")):
+        names |= set(re.findall(r'env_knob\("(SKY_[A-Z0-9_]+)"', open(f).read()))
+    assert names, "no env_knob call found: the scan is broken"
+    assert names <= set(bench.KNOBS), f"knobs missing from bench.KNOBS: {sorted(names - set(bench.KNOBS))}"
