@@ -643,9 +643,9 @@ static int pixel_impl(sky_bank_t* b, const float* q, const unsigned char* qmask,
     SearchState s{};
     if (emit) {
         if (n_items == 0) return SKY_OK;
-        return launch_pixel_search(b, qp, excl, Q, item0, item0 + n_items, s, pixel_grid(b, n_items), qc, emit, st);
+        return launch_pixel_search(b, qp, excl, Q, item0, item0 + n_items, s, pixel_grid(b, n_items, qc), qc, emit, st);
     }
-    const int grid = pixel_grid(b, b->rows);
+    const int grid = pixel_grid(b, b->rows, qc);
     rc = plan_state(b, grid, Q, k, grid, &s);
     if (rc) return rc;
     rc = launch_init_state(s, grid, st);

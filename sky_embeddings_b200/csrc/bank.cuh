@@ -95,7 +95,7 @@ int launch_stream_search(const sky_bank* b, const SimtArgs& a, const SearchState
 
 // pixel_search.cu
 int pixel_pick_qc(int Q);
-int pixel_grid(const sky_bank* b, int64_t n_rows);
+int pixel_grid(const sky_bank* b, int64_t n_rows, int qc);
 int launch_pixel_fold(const float* q, const unsigned char* mask, int64_t n, int D, float* qp, int* excl, cudaStream_t st);
 int launch_pixel_search(const sky_bank* b, const float* qp, const int* excl, int Q, int64_t row_lo, int64_t row_hi,
                         const SearchState& s, int grid, int qc, float* emit, cudaStream_t st);

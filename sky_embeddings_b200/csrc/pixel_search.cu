@@ -24,15 +24,15 @@
 
 namespace sky {
 
-constexpr int kPxWarps = 8;
-constexpr int kPxConsumers = kPxWarps * 32;
-constexpr int kPxThreads = kPxConsumers + 64;      // + producer warp + exchange warp
-constexpr int kPxProducerWarp = kPxWarps;
-constexpr int kPxXchgWarp = kPxWarps + 1;
 constexpr int kPxChunk = 16384;                    // bytes per stage
 constexpr int kPxChunkElems = kPxChunk / 4;
-constexpr int kPxRows = 8;                         // rows per group (= consumer warps: warp w finishes row w)
 constexpr int kPxMaxStages = 13;
+// Two shapes of the consumer side (template parameters WARPS, ROWS of the kernel):
+//   8 warps x 8 rows per group: a lane keeps 16 pixels of q' per query in registers for 8 rows -- one or two queries
+//     per pass run at the HBM roofline with it;
+//   16 warps x 4 rows per group (four queries per pass): half the pixels per lane, so the registers allow twice the
+//     warps -- at 16 instructions per pixel the kernel is bound by issue latency, and 4 warps per scheduler hide what 2 cannot.
+constexpr int kPxMaxWarps = 16;
 
 struct PixelParams {
     const unsigned char* bank;   // [rows][D] fp32, row-major
@@ -66,8 +66,13 @@ __device__ __forceinline__ void px_bulk_load(uint32_t smem_dst, const void* gsrc
         : "memory");
 }
 
-template <int QC>
-__global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const PixelParams p) {
+template <int QC, int WARPS, int ROWS>
+__global__ void __launch_bounds__(WARPS * 32 + 64, 1) pixel_search_kernel(const PixelParams p) {
+    constexpr int kPxWarps = WARPS, kPxRows = ROWS;                 // rows per group <= consumer warps: warp w finishes row w
+    constexpr int kPxConsumers = WARPS * 32;
+    constexpr int kPxProducerWarp = WARPS, kPxXchgWarp = WARPS + 1; // + producer warp + exchange warp
+    constexpr int NJ = kPxChunkElems / (WARPS * 128);               // float4 per lane and piece (4 or 2)
+    static_assert(ROWS <= WARPS && NJ * WARPS * 128 == kPxChunkElems, "consumer shape");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int S = p.stages;
@@ -148,8 +153,8 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
         }
     } else if (warp < kPxWarps) {
         const uint32_t stage0 = ptx::smem_u32(sStage);
-        // this lane's 16 elements of a piece: 4 x float4 at element warp*512 + j*128 + lane*4
-        const int e0 = warp * 512 + lane * 4;
+        // this lane's elements of a piece: NJ x float4 at element warp * NJ * 128 + j * 128 + lane * 4
+        const int e0 = warp * (NJ * 128) + lane * 4;
         int stage = 0;
         uint32_t phase = 0;
         for (int g = 0; g < my_groups; ++g) {
@@ -168,11 +173,11 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
             for (int c = 0; c < p.nch; ++c) {
                 const int len = (c == p.nch - 1) ? last_len : kPxChunkElems;
                 // slice of the folded queries for this piece (L2 / L1 resident), excluded = NaN
-                float4 qv[QC][4];
+                float4 qv[QC][NJ];
 #pragma unroll
                 for (int q = 0; q < QC; ++q)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < NJ; ++j) {
                         const int e = e0 + j * 128;
                         if (q < p.nq && e < len)
                             qv[q][j] = __ldg(reinterpret_cast<const float4*>(p.qp + static_cast<size_t>(p.q0 + q) * p.D +
@@ -186,9 +191,9 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
                     if (r < rows) {
                         ptx::mbar_wait_relaxed(&full_bar[stage], phase, 20);
                         const uint32_t src = stage0 + static_cast<uint32_t>(stage) * kPxChunk + e0 * 4;
-                        float4 xv[4];
+                        float4 xv[NJ];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < NJ; ++j) {
                             // beyond the end of a short last piece the ring holds stale data: q' is NaN there
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                          : "=f"(xv[j].x), "=f"(xv[j].y), "=f"(xv[j].z), "=f"(xv[j].w) : "r"(src + j * 512));
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
                             // 2 instructions per pixel and query (subtract, predicated multiply-add) + a test and a
                             // count per pixel, instead of 4 per pixel and query
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
+                            for (int j = 0; j < NJ; ++j) {
                                 const bool in = e0 + j * 128 < len;      // a short last piece: stale ring data beyond it
                                 const bool p0 = in && xv[j].x == xv[j].x, p1 = in && xv[j].y == xv[j].y;
                                 const bool p2 = in && xv[j].z == xv[j].z, p3 = in && xv[j].w == xv[j].w;
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
 #pragma unroll
                             for (int q = 0; q < QC; ++q)
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
+                                for (int j = 0; j < NJ; ++j) {
                                     const float d0 = qv[q][j].x - xv[j].x, d1 = qv[q][j].y - xv[j].y;
                                     const float d2 = qv[q][j].z - xv[j].z, d3 = qv[q][j].w - xv[j].w;
                                     // NaN (either side missing or masked out) drops out of both sums
@@ -296,11 +301,18 @@ __global__ void __launch_bounds__(kPxThreads, 1) pixel_search_kernel(const Pixel
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// consumer shape by queries per pass (see the top of the file)
+constexpr int kPxUseWide = 1;      // four queries per pass: 16 warps x 4 rows (0: 8 x 8 as for one or two queries)
+static bool px_wide(int qc) { return qc == 4 && env_knob("SKY_PX_WIDE", kPxUseWide) != 0; }
+static int px_warps(int qc) { return px_wide(qc) ? 16 : 8; }
+static int px_rows(int qc) { return px_wide(qc) ? 4 : 8; }
+
 static size_t px_fixed_bytes(int qc) {
-    size_t b = static_cast<size_t>(kPxWarps) * kPxRows * qc * 2 * sizeof(float);
+    const int warps = px_warps(qc), rows = px_rows(qc);
+    size_t b = static_cast<size_t>(warps) * rows * qc * 2 * sizeof(float);
     b += 2 * kPxMaxStages * sizeof(uint64_t);
     b += qc * (sizeof(unsigned long long) + sizeof(float) + sizeof(int) + sizeof(uint32_t));
-    b += kPxWarps * 256 * sizeof(uint32_t) + 16;
+    b += warps * 256 * sizeof(uint32_t) + 16;
     return b + 256;
 }
 
@@ -310,8 +322,9 @@ int pixel_pick_qc(int Q) {
     return Q == 1 ? 1 : (Q == 2 ? 2 : 4);
 }
 
-int pixel_grid(const sky_bank* b, int64_t n_rows) {
-    const int64_t groups = (n_rows + kPxRows - 1) / kPxRows;
+int pixel_grid(const sky_bank* b, int64_t n_rows, int qc) {
+    const int rows = px_rows(qc);
+    const int64_t groups = (n_rows + rows - 1) / rows;
     int64_t g = groups < b->num_sms ? groups : b->num_sms;
     return static_cast<int>(g < 1 ? 1 : g);
 }
@@ -323,10 +336,10 @@ int launch_pixel_fold(const float* q, const unsigned char* mask, int64_t n, int 
     return SKY_OK;
 }
 
-template <int QC>
+template <int QC, int WARPS, int ROWS>
 static int pixel_launch_one(const PixelParams& p, int grid, size_t smem, cudaStream_t st) {
-    SKY_CUDA(cudaFuncSetAttribute(pixel_search_kernel<QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    pixel_search_kernel<QC><<<grid, kPxThreads, smem, st>>>(p);
+    SKY_CUDA(cudaFuncSetAttribute(pixel_search_kernel<QC, WARPS, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    pixel_search_kernel<QC, WARPS, ROWS><<<grid, WARPS * 32 + 64, smem, st>>>(p);
     SKY_LAUNCH_CHECK("pixel_search_kernel");
     return SKY_OK;
 }
@@ -334,7 +347,8 @@ static int pixel_launch_one(const PixelParams& p, int grid, size_t smem, cudaStr
 // qp: folded queries [Q][D]; rows [row_lo, row_hi) of the bank; emit != null -> scores only
 int launch_pixel_search(const sky_bank* b, const float* qp, const int* excl, int Q, int64_t row_lo, int64_t row_hi,
                         const SearchState& s, int grid, int qc, float* emit, cudaStream_t st) {
-    int stages = kPxMaxStages;
+    int stages = static_cast<int>((227 * 1024 - px_fixed_bytes(qc)) / kPxChunk);
+    if (stages > kPxMaxStages) stages = kPxMaxStages;
     { const int e = env_knob("SKY_PX_STAGES", 0); if (e >= 2 && e < stages) stages = e; }
     const size_t smem = static_cast<size_t>(stages) * kPxChunk + px_fixed_bytes(qc);
     for (int q0 = 0; q0 < Q; q0 += qc) {
@@ -351,8 +365,9 @@ int launch_pixel_search(const sky_bank* b, const float* qp, const int* excl, int
         p.p_stride = s.p_stride; p.Qtot = s.Qtot; p.cap = s.cap; p.k = s.k; p.use_gtau = s.use_gtau;
         p.emit = emit; p.emit_item0 = row_lo; p.emit_n = row_hi - row_lo;
         if (!emit) prof_mark(b, st);
-        int rc = qc == 1 ? pixel_launch_one<1>(p, grid, smem, st)
-                         : (qc == 2 ? pixel_launch_one<2>(p, grid, smem, st) : pixel_launch_one<4>(p, grid, smem, st));
+        int rc = qc == 1 ? pixel_launch_one<1, 8, 8>(p, grid, smem, st)
+                         : (qc == 2 ? pixel_launch_one<2, 8, 8>(p, grid, smem, st)
+                                    : (px_wide(qc) ? pixel_launch_one<4, 16, 4>(p, grid, smem, st) : pixel_launch_one<4, 8, 8>(p, grid, smem, st)));
         if (!emit) prof_mark(b, st);
         if (rc) return rc;
     }

@@ -568,10 +568,10 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
 
 // Warp-per-query merge of one LATER phase (k <= 128): the carry is sorted, the phase's survivors are few (~k ln 5 per
 // query), so one warp ranks them with binary searches instead of a 256-thread CTA paying six dependent L2 round trips
-// per query -- eight queries per CTA, one wave over the GPU.  A query with more survivors than a warp holds is flagged
+// per query -- four queries per CTA.  A query with more survivors than a warp holds is flagged
 // in `slow` and left (untouched) to merge_phase_kernel.
-constexpr int kMwWarps = 8;
-constexpr int kMwMaxM = 256;
+constexpr int kMwWarps = 4;
+constexpr int kMwMaxM = 512;         // a phase lets k * (rows of the phase / rows before it) <= ~3.2 k survivors per query through: 320 at k = 100
 constexpr int kMwMaxK = 128;
 constexpr int kMwMaxPL = 8;          // lists per lane: P <= 256
 __global__ void __launch_bounds__(kMwWarps * 32)
