@@ -66,6 +66,19 @@ __device__ __forceinline__ void px_bulk_load(uint32_t smem_dst, const void* gsrc
         : "memory");
 }
 
+// One pixel of one query on the general path: acc += d * d and n += 1 unless d is NaN.  Written as PTX so that it stays
+// FSETP + predicated FFMA + predicated integer add: the fp32 pipe and the ALU pipe each issue a warp instruction every
+// other cycle (B300_MICROARCH.md, "Pipe rates"), so with the subtraction in front this is two instructions on either pipe.
+// The compiler's own forms were worse: an integer count under `if` became add + select (three ALU instructions per pixel
+// and query: ALU-bound at 0.51 of the HBM roofline), a float count three fp32-pipe instructions (0.59).
+__device__ __forceinline__ void px_accumulate(float d, float& acc, int& n) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.eq.f32 p, %2, %2;\n\t"
+        "@p fma.rn.f32 %0, %2, %2, %0;\n\t"
+        "@p add.s32 %1, %1, 1;\n\t}"
+        : "+f"(acc), "+r"(n) : "f"(d));
+}
+
 template <int QC, int WARPS, int ROWS>
 __global__ void __launch_bounds__(WARPS * 32 + 64, 1) pixel_search_kernel(const PixelParams p) {
     constexpr int kPxWarps = WARPS, kPxRows = ROWS;                 // rows per group <= consumer warps: warp w finishes row w
@@ -160,15 +173,12 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) pixel_search_kernel(const 
         for (int g = 0; g < my_groups; ++g) {
             const int64_t r0 = p.row_lo + (blockIdx.x + static_cast<int64_t>(g) * gridDim.x) * kPxRows;
             const int rows = static_cast<int>(p.row_hi - r0 < kPxRows ? p.row_hi - r0 : kPxRows);
-            // the pixel counts are kept as floats (exact: a row has 20480 < 2^24 pixels): a predicated FADD on the
-            // fp32 pipe next to the predicated FFMA, where an integer count costs two ALU-pipe instructions per
-            // pixel and query (add + select) and made the general path ALU-bound at 4 queries per pass
             float acc[kPxRows][QC];
-            float cnt[kPxRows][QC];
+            int cntg[kPxRows][QC];       // pixels that took part, per query (clean path: slot 0 serves every query)
 #pragma unroll
             for (int r = 0; r < kPxRows; ++r)
 #pragma unroll
-                for (int q = 0; q < QC; ++q) { acc[r][q] = 0.f; cnt[r][q] = 0.f; }
+                for (int q = 0; q < QC; ++q) { acc[r][q] = 0.f; cntg[r][q] = 0; }
 
             for (int c = 0; c < p.nch; ++c) {
                 const int len = (c == p.nch - 1) ? last_len : kPxChunkElems;
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) pixel_search_kernel(const 
                                 const bool in = e0 + j * 128 < len;      // a short last piece: stale ring data beyond it
                                 const bool p0 = in && xv[j].x == xv[j].x, p1 = in && xv[j].y == xv[j].y;
                                 const bool p2 = in && xv[j].z == xv[j].z, p3 = in && xv[j].w == xv[j].w;
-                                cnt[r][0] += static_cast<float>((p0 ? 1 : 0) + (p1 ? 1 : 0) + (p2 ? 1 : 0) + (p3 ? 1 : 0));
+                                cntg[r][0] += (p0 ? 1 : 0) + (p1 ? 1 : 0) + (p2 ? 1 : 0) + (p3 ? 1 : 0);
 #pragma unroll
                                 for (int q = 0; q < QC; ++q) {
                                     const float d0 = qv[q][j].x - xv[j].x, d1 = qv[q][j].y - xv[j].y;
@@ -225,10 +235,10 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) pixel_search_kernel(const 
                                     const float d0 = qv[q][j].x - xv[j].x, d1 = qv[q][j].y - xv[j].y;
                                     const float d2 = qv[q][j].z - xv[j].z, d3 = qv[q][j].w - xv[j].w;
                                     // NaN (either side missing or masked out) drops out of both sums
-                                    if (d0 == d0) { acc[r][q] = fmaf(d0, d0, acc[r][q]); cnt[r][q] += 1.f; }
-                                    if (d1 == d1) { acc[r][q] = fmaf(d1, d1, acc[r][q]); cnt[r][q] += 1.f; }
-                                    if (d2 == d2) { acc[r][q] = fmaf(d2, d2, acc[r][q]); cnt[r][q] += 1.f; }
-                                    if (d3 == d3) { acc[r][q] = fmaf(d3, d3, acc[r][q]); cnt[r][q] += 1.f; }
+                                    px_accumulate(d0, acc[r][q], cntg[r][q]);
+                                    px_accumulate(d1, acc[r][q], cntg[r][q]);
+                                    px_accumulate(d2, acc[r][q], cntg[r][q]);
+                                    px_accumulate(d3, acc[r][q], cntg[r][q]);
                                 }
                         }
                         __syncwarp();
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) pixel_search_kernel(const 
 #pragma unroll
                 for (int q = 0; q < QC; ++q) {
                     float a = acc[r][q];
-                    float n = clean ? cnt[r][0] : cnt[r][q];
+                    int n = clean ? cntg[r][0] : cntg[r][q];
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) {
                         a += __shfl_xor_sync(0xffffffffu, a, off);
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) pixel_search_kernel(const 
                     }
                     if (lane == 0) {
                         sPart[((warp * kPxRows + r) * QC + q) * 2] = a;
-                        sPart[((warp * kPxRows + r) * QC + q) * 2 + 1] = n;
+                        sPart[((warp * kPxRows + r) * QC + q) * 2 + 1] = static_cast<float>(n);
                     }
                 }
             ptx::named_bar_sync(1, kPxConsumers);
@@ -302,7 +312,7 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) pixel_search_kernel(const 
 // host side
 // ---------------------------------------------------------------------------------------------
 // consumer shape by queries per pass (see the top of the file)
-constexpr int kPxUseWide = 1;      // four queries per pass: 16 warps x 4 rows (0: 8 x 8 as for one or two queries)
+constexpr int kPxUseWide = 0;      // four queries per pass: 16 warps x 4 rows (0: 8 x 8 as for one or two queries)
 static bool px_wide(int qc) { return qc == 4 && env_knob("SKY_PX_WIDE", kPxUseWide) != 0; }
 static int px_warps(int qc) { return px_wide(qc) ? 16 : 8; }
 static int px_rows(int qc) { return px_wide(qc) ? 4 : 8; }

@@ -755,6 +755,7 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     int t0 = 0;
     int per_cta = 1;
     bool first = true;
+    int phase_idx = 0;
     int growth = 4;       // phase sizes 1, 1, 4, 16, ... tiles per CTA (measured: growth 16 saves two merges on a small shard but its
                           // k ln 17 survivors per query overflow lists and pools at k = 1000: C4's share 20 -> 29 ms)
     { const int e = env_knob("SKY_TB_PHASE0", 0); if (e >= 1) per_cta = e; }
@@ -770,6 +771,9 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
         batch_bounds_kernel<<<(Qp + 255) / 256, 256, 0, st>>>(tauc, qconst, Q, Qp, metric, dd, b1, b2);
         SKY_LAUNCH_CHECK("batch_bounds_kernel");
         p.tile0 = t0; p.tile1 = t1;
+        { const int tp = env_knob("SKY_TB_TRACE_PHASE", -1);      // experiments: timeline (debug bit 5) of one phase only
+          if (tp >= 0) p.debug = (env_knob("SKY_TB_DEBUG", 0) & ~32) | (phase_idx == tp ? 32 : 0); }
+        ++phase_idx;
         // dense first phase: one tile per CTA into empty lists (a longer first phase keeps the filtered path)
         p.dense = (first && per_cta == 1 && t1 - t0 <= P) ? 1 : 0;
         const int grid = (t1 - t0) < P ? (t1 - t0) : P;
