@@ -66,7 +66,7 @@ WORKLOADS = {
 PIXEL_WORKLOADS = {"c5": (1_000_000, 4, 100), "c5s": (100_000, 4, 100), "c5q1": (1_000_000, 1, 100), "c5q1s": (100_000, 1, 100)}
 ALSO_N1 = ["c2w", "q1w", "c3", "c5q1"]
 ALSO_MULTI = ["c3", "c4"]
-KNOBS = ("SKY_PDL", "SKY_PX_QC", "SKY_PX_STAGES", "SKY_PX_WIDE", "SKY_SCORE_GENERIC", "SKY_ST_DEBUG", "SKY_ST_POLICY", "SKY_ST_SPIN",
+KNOBS = ("SKY_PDL", "SKY_PX_QC", "SKY_PX_STAGES", "SKY_SCORE_GENERIC", "SKY_ST_DEBUG", "SKY_ST_POLICY", "SKY_ST_SPIN",
          "SKY_ST_SPLIT", "SKY_ST_STAGES", "SKY_TB_DEBUG", "SKY_TB_DENSE0", "SKY_TB_GROWTH", "SKY_TB_PHASE0", "SKY_TB_SORTED", "SKY_TB_TRACE_PHASE", "SKY_TC_DEBUG",
          "SKY_TC_GRID", "SKY_TC_POLICY", "SKY_TC_STAGES", "SKY_TC_TMA", "SKY_TW2_OCC", "SKY_TW2_POLICY", "SKY_TW2_SPIN",
          "SKY_TW2_STAGES", "SKY_TW_DEBUG", "SKY_TW_PAIR")

@@ -27,12 +27,11 @@ namespace sky {
 constexpr int kPxChunk = 16384;                    // bytes per stage
 constexpr int kPxChunkElems = kPxChunk / 4;
 constexpr int kPxMaxStages = 13;
-// Two shapes of the consumer side (template parameters WARPS, ROWS of the kernel):
-//   8 warps x 8 rows per group: a lane keeps 16 pixels of q' per query in registers for 8 rows -- one or two queries
-//     per pass run at the HBM roofline with it;
-//   16 warps x 4 rows per group (four queries per pass): half the pixels per lane, so the registers allow twice the
-//     warps -- at 16 instructions per pixel the kernel is bound by issue latency, and 4 warps per scheduler hide what 2 cannot.
-constexpr int kPxMaxWarps = 16;
+// Consumer shape (template parameters WARPS, ROWS of the kernel): 8 warps x 8 rows per group -- a lane keeps 16 pixels of
+// q' per query in registers for 8 rows.  One or two queries per pass run at the HBM roofline.  Four queries per pass
+// need 16 instructions per pixel and the SM issues ~0.47 warp instructions per scheduler and cycle whatever the mix
+// (measured: integer counts 24.7 ms per 1 M cutouts, float counts 21.3, the PTX form below 21.8; 16 warps x 4 rows with
+// half the pixels per lane 22.3 -- more warps do not help, it is not latency): 0.58 of the HBM roofline is the issue limit.
 
 struct PixelParams {
     const unsigned char* bank;   // [rows][D] fp32, row-major
@@ -67,10 +66,9 @@ __device__ __forceinline__ void px_bulk_load(uint32_t smem_dst, const void* gsrc
 }
 
 // One pixel of one query on the general path: acc += d * d and n += 1 unless d is NaN.  Written as PTX so that it stays
-// FSETP + predicated FFMA + predicated integer add: the fp32 pipe and the ALU pipe each issue a warp instruction every
-// other cycle (B300_MICROARCH.md, "Pipe rates"), so with the subtraction in front this is two instructions on either pipe.
-// The compiler's own forms were worse: an integer count under `if` became add + select (three ALU instructions per pixel
-// and query: ALU-bound at 0.51 of the HBM roofline), a float count three fp32-pipe instructions (0.59).
+// FSETP + predicated FFMA + predicated integer add (with the subtraction in front: four instructions per pixel and query,
+// two on the fp32 pipe and two on the ALU pipe).  Left to the compiler, an integer count under `if` became add + select
+// (five instructions, three of them on the ALU pipe: 0.51 of the HBM roofline at four queries per pass against 0.58).
 __device__ __forceinline__ void px_accumulate(float d, float& acc, int& n) {
     asm("{\n\t.reg .pred p;\n\t"
         "setp.eq.f32 p, %2, %2;\n\t"
@@ -311,11 +309,8 @@ __global__ void __launch_bounds__(WARPS * 32 + 64, 1) pixel_search_kernel(const 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// consumer shape by queries per pass (see the top of the file)
-constexpr int kPxUseWide = 0;      // four queries per pass: 16 warps x 4 rows (0: 8 x 8 as for one or two queries)
-static bool px_wide(int qc) { return qc == 4 && env_knob("SKY_PX_WIDE", kPxUseWide) != 0; }
-static int px_warps(int qc) { return px_wide(qc) ? 16 : 8; }
-static int px_rows(int qc) { return px_wide(qc) ? 4 : 8; }
+static int px_warps(int) { return 8; }
+static int px_rows(int) { return 8; }
 
 static size_t px_fixed_bytes(int qc) {
     const int warps = px_warps(qc), rows = px_rows(qc);
@@ -376,8 +371,7 @@ int launch_pixel_search(const sky_bank* b, const float* qp, const int* excl, int
         p.emit = emit; p.emit_item0 = row_lo; p.emit_n = row_hi - row_lo;
         if (!emit) prof_mark(b, st);
         int rc = qc == 1 ? pixel_launch_one<1, 8, 8>(p, grid, smem, st)
-                         : (qc == 2 ? pixel_launch_one<2, 8, 8>(p, grid, smem, st)
-                                    : (px_wide(qc) ? pixel_launch_one<4, 16, 4>(p, grid, smem, st) : pixel_launch_one<4, 8, 8>(p, grid, smem, st)));
+                         : (qc == 2 ? pixel_launch_one<2, 8, 8>(p, grid, smem, st) : pixel_launch_one<4, 8, 8>(p, grid, smem, st));
         if (!emit) prof_mark(b, st);
         if (rc) return rc;
     }

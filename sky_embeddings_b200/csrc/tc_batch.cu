@@ -24,13 +24,21 @@
 namespace sky {
 
 constexpr int kTbBN = 256;                     // queries per tile (UMMA N)
-constexpr int kTbThreads = 6 * 32;             // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kTbEpiThreads = 128;
+// Warp 0 TMA, warp 1 MMA, warps 2-9 epilogue.  EIGHT epilogue warps: a warp may only read the tensor-memory lanes of
+// its quarter (warp % 4), so two warps share each quarter and split the accumulator's 256 columns.  With four warps the
+// filter of a visit took ~4.7 k cycles + ~1 k of write-back against the 6.1 k cycles of its MMAs (%clock timeline of
+// CTA 0, tools/trace_tb_phase.py): the kernel was epilogue-bound even without survivors.
+constexpr int kTbEpiWarps = 8;
+constexpr int kTbThreads = (2 + kTbEpiWarps) * 32;
+constexpr int kTbEpiThreads = kTbEpiWarps * 32;
+constexpr int kTbQPT = kTbBN / kTbEpiThreads;                 // queries of a group staged per epilogue thread (1)
+constexpr int kTbWarpChunks = (kTbBN / 32) / (kTbEpiWarps / 4);   // 32-column chunks per warp and visit (4)
+static_assert(kTbQPT * kTbEpiThreads == kTbBN && kTbWarpChunks % 2 == 0 && kTbBN / kTbEpiWarps == 32, "epilogue shape");
 constexpr int kTbStageA = kTileRows * 128;     // 16 KB: 128 rows x 64 bf16
 constexpr int kTbStageB = kTbBN * 128;         // 32 KB: 256 queries x 64 bf16
 constexpr int kTbStage = kTbStageA + kTbStageB;
 constexpr int kTbStages = 4;
-constexpr int kTbQueue = 512;                  // survivor queue entries per epilogue warp (4 x 4 KB of shared memory)
+constexpr int kTbQueue = 192;                  // survivor queue entries per epilogue warp (8 x 1.5 KB of shared memory)
 
 struct TbParams {
     const float* rownorm;      // [rows_pad]
@@ -68,7 +76,7 @@ __device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
 #ifdef SKY_EXPERIMENTS
 constexpr int kTbTrace = 4096;
 __device__ long long g_tb_trace[kTbTrace * 4 * 5];
-#define TB_TRACE(slot, val) do { if ((SKY_DBG(p) & 32) && blockIdx.x == 0 && lane == 0 && v < kTbTrace) g_tb_trace[(v * 4 + e) * 5 + (slot)] = (val); } while (0)
+#define TB_TRACE(slot, val) do { if ((SKY_DBG(p) & 32) && blockIdx.x == 0 && lane == 0 && v < kTbTrace && e < 4) g_tb_trace[(v * 4 + e) * 5 + (slot)] = (val); } while (0)
 #else
 #define TB_TRACE(slot, val) do { } while (0)
 #endif
@@ -99,9 +107,9 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     float* sB2 = sB1 + 2 * kTbBN;                                                   // [2][256]
     float* sQc = sB2 + 2 * kTbBN;                                                   // [2][256] |t| or |t|^2
     int* sCnt = reinterpret_cast<int*>(sQc + 2 * kTbBN);                            // [2][256] list fill of this CTA
-    uint32_t* sHist = reinterpret_cast<uint32_t*>(sCnt + 2 * kTbBN);                // [4][256]
-    uint2* sQueue = reinterpret_cast<uint2*>(sHist + 4 * 256);                      // [4][kTbQueue] survivors of a visit
-    uint32_t* sTmemBase = reinterpret_cast<uint32_t*>(sQueue + 4 * kTbQueue);
+    uint32_t* sHist = reinterpret_cast<uint32_t*>(sCnt + 2 * kTbBN);                // [epilogue warps][256]
+    uint2* sQueue = reinterpret_cast<uint2*>(sHist + kTbEpiWarps * 256);            // [epilogue warps][kTbQueue] survivors of a visit
+    uint32_t* sTmemBase = reinterpret_cast<uint32_t*>(sQueue + kTbEpiWarps * kTbQueue);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr bool largest = COS;
@@ -116,7 +124,7 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
         for (int s = 0; s < kTbStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], kTbEpiWarps); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -186,10 +194,11 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
         }
     } else {
-        // ===================== epilogue: 4 warps, warp & 3 = TMEM lane quarter =====================
-        const int e = warp - 2;                   // 0..3: histogram slot, prune ownership
+        // ===================== epilogue: 8 warps, warp & 3 = TMEM lane quarter, e / 4 = column half =====================
+        const int e = warp - 2;                   // 0..7: histogram slot, queue, prune ownership
         const int quarter = warp & 3;
-        const int et = tid - 64;                  // 0..127
+        const int c_lo = (e >> 2) * kTbWarpChunks;   // first 32-column chunk of this warp
+        const int et = tid - 64;                  // 0..255
         const uint32_t hist = smem_addr(sHist + e * 256);
         uint64_t* my_lists = p.lists + static_cast<size_t>(blockIdx.x) * p.Qp * p.cap;
         int* my_counts = p.counts + static_cast<size_t>(blockIdx.x) * p.Qp;
@@ -197,14 +206,14 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
         // per-query state of a visit's query group is staged in shared memory: pre-filter coefficients, |t|,
         // the exact bound max(global k-th best, CTA-local bound) and the fill of this CTA's list.  It is
-        // prefetched into registers one visit ahead (thread et owns queries et and et + 128 of the group).
-        float nb1[2], nb2[2], nqc[2];
-        unsigned long long ntau[2];
-        int ncnt[2];
+        // prefetched into registers one visit ahead (thread et owns query et of the group).
+        float nb1[kTbQPT], nb2[kTbQPT], nqc[kTbQPT];
+        unsigned long long ntau[kTbQPT];
+        int ncnt[kTbQPT];
         auto prefetch_group = [&](int gq) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int q = gq * kTbBN + et + j * 128;
+            for (int j = 0; j < kTbQPT; ++j) {
+                const int q = gq * kTbBN + et + j * kTbEpiThreads;
                 nb1[j] = __ldg(p.bound1 + q); nb2[j] = __ldg(p.bound2 + q); nqc[j] = __ldg(p.qconst + q);
                 const unsigned long long tg = __ldg(reinterpret_cast<const unsigned long long*>(p.tauc + q));
                 const unsigned long long tl = ld_cg_u64(my_lthr + q);
@@ -224,8 +233,8 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t acc_phase = (v >> 1) & 1;
             const int buf = v & 1;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int i = buf * kTbBN + et + j * 128;
+            for (int j = 0; j < kTbQPT; ++j) {
+                const int i = buf * kTbBN + et + j * kTbEpiThreads;
                 sB1[i] = nb1[j]; sB2[i] = nb2[j]; sQc[i] = nqc[j]; sTau[i] = ntau[j]; sCnt[i] = ncnt[j];
             }
             // the next group is a different set of queries, except when there is a single group: then its
@@ -346,23 +355,24 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     qn += __popc(act);
                 }
             };
-            // software pipeline over the 8 chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c is filtered
+            // software pipeline over this warp's chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c is filtered
             uint32_t va[32], vb[32];
-            ptx::tmem_ld_32x32b_x32(taddr, va);
+            ptx::tmem_ld_32x32b_x32(taddr + c_lo * 32, va);
 #pragma unroll 1
-            for (int c2 = 0; c2 < kTbBN / 64; ++c2) {
+            for (int c2 = 0; c2 < kTbWarpChunks / 2; ++c2) {
+                const int c = c_lo + 2 * c2;
                 tmem_ld_wait_touch(va);
-                ptx::tmem_ld_32x32b_x32(taddr + (2 * c2 + 1) * 32, vb);
-                if (!(SKY_DBG(p) & 1)) process(va, 2 * c2);
+                ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
+                if (!(SKY_DBG(p) & 1)) process(va, c);
                 tmem_ld_wait_touch(vb);
-                if (c2 + 1 < kTbBN / 64) {
-                    ptx::tmem_ld_32x32b_x32(taddr + (2 * c2 + 2) * 32, va);
-                } else {                                      // accumulator fully in registers: hand it back
+                if (c2 + 1 < kTbWarpChunks / 2) {
+                    ptx::tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
+                } else {                                      // this warp's share of the accumulator is in registers: hand it back
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
                 }
-                if (!(SKY_DBG(p) & 1)) process(vb, 2 * c2 + 1);
+                if (!(SKY_DBG(p) & 1)) process(vb, c + 1);
             }
             if (!p.dense) drain();
             TB_TRACE(2, clock64());
@@ -371,18 +381,17 @@ tc_batch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             // to their k best (rare once bounds exist), which also yields a CTA-local bound
             if (p.dense) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) st_cg_i32(my_counts + g * kTbBN + et + j * 128, kTileRows);
+                for (int j = 0; j < kTbQPT; ++j) st_cg_i32(my_counts + g * kTbBN + et + j * kTbEpiThreads, kTileRows);
             } else if (!(SKY_DBG(p) & 8) && named_bar_or(3, kTbEpiThreads, inserted)) {
-                // warp e owns queries [64 e, 64 e + 64) of the group; lane handles two of them
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int qq = e * 64 + h * 32 + lane;
+                // warp e owns queries [32 e, 32 e + 32) of the group, one per lane
+                {
+                    const int qq = e * 32 + lane;
                     const int n = sCnt[buf * kTbBN + qq];
                     uint32_t full = __ballot_sync(0xffffffffu, n > p.cap - kTileRows);
                     while (full) {                                  // rare: prune one list per iteration, whole warp
                         const int l = __ffs(full) - 1;
                         full &= full - 1;
-                        const int qf = e * 64 + h * 32 + l;
+                        const int qf = e * 32 + l;
                         const int nf = __shfl_sync(0xffffffffu, n, l);
                         uint64_t* lst = my_lists + static_cast<size_t>(g * kTbBN + qf) * p.cap;
                         const uint64_t kth = warp_select_kth(lst, nf, p.k, hist);
@@ -737,7 +746,7 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
     rc = make_tmap_2d(&tmq, bq, Qp, b->Dp, kTbBN);
     if (rc) return rc;
 
-    const size_t smem = 1024 + static_cast<size_t>(kTbStages) * kTbStage + (2 * kTbStages + 4) * 8 + 2 * kTbBN * 8 + 8 * kTbBN * 4 + 4 * 256 * 4 + 4 * kTbQueue * 8 + 64;
+    const size_t smem = 1024 + static_cast<size_t>(kTbStages) * kTbStage + (2 * kTbStages + 4) * 8 + 2 * kTbBN * 8 + 8 * kTbBN * 4 + kTbEpiWarps * 256 * 4 + kTbEpiWarps * kTbQueue * 8 + 64;
     SKY_CUDA(cudaFuncSetAttribute(tc_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SKY_CUDA(cudaFuncSetAttribute(tc_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SKY_CUDA(cudaFuncSetAttribute(merge_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
