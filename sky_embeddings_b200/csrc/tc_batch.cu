@@ -496,11 +496,42 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
     }
     __syncthreads();
     const int np = static_cast<int>(npool);          // all candidates: carry + every list
-    // gather: everything if it fits the pool, else the first kMpPool candidates (a sample)
-    for (int p = warp; p < P; p += nwarps) {
-        const int n = s_n[p], o = s_off[p];
-        const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
-        for (int i = lane; i < n && o + i < kMpPool; i += 32) pool[o + i] = e[i];
+    // gather: everything if it fits the pool, else the first kMpPool candidates (a sample).  Four independent loads
+    // per lane and step: a dependent one-load-per-lane loop leaves ~6 KB in flight per SM and the merge of the dense first
+    // phase (19 k candidates per query, 620 MB over C3's queries) crawled at 0.7 TB/s.
+    if (P <= kMpThreads && np <= 32 * P) {
+        // later phases: a handful of survivors per list.  One THREAD per list, four loads in flight each: ~n / 4 L2 round
+        // trips for the whole query instead of one per list and warp (P / 8 of them, one after the other)
+        if (tid < P) {
+            const int n = s_n[tid], o = s_off[tid];
+            const uint64_t* e = lists + (static_cast<size_t>(tid) * Qp + q) * cap;
+            for (int i0 = 0; i0 < n && o + i0 < kMpPool; i0 += 4) {
+                uint64_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = (i0 + u < n && o + i0 + u < kMpPool) ? ld_cg_u64(e + i0 + u) : 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (i0 + u < n && o + i0 + u < kMpPool) pool[o + i0 + u] = v[u];
+            }
+        }
+    } else {
+        for (int p = warp; p < P; p += nwarps) {
+            const int n = s_n[p], o = s_off[p];
+            if (o >= kMpPool) continue;
+            const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
+            for (int i0 = 0; i0 < n && o + i0 < kMpPool; i0 += 128) {
+                uint64_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 32 + lane;
+                    v[u] = (i < n && o + i < kMpPool) ? ld_cg_u64(e + i) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 32 + lane;
+                    if (i < n && o + i < kMpPool) pool[o + i] = v[u];
+                }
+            }
+        }
     }
     __syncthreads();
     bool done = false;
@@ -530,12 +561,30 @@ merge_phase_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tauc, co
                 const uint64_t v = cq[j];
                 if (v >= tau0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < static_cast<uint32_t>(nsample)) extra[pos] = v; }
             }
-            for (int p = warp; p < P; p += nwarps) {
-                const int n = s_n[p];
-                const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
-                for (int i = lane; i < n; i += 32) {
-                    const uint64_t v = e[i];
-                    if (v >= tau0) { const uint32_t pos = atomicAdd(&nkeep, 1u); if (pos < static_cast<uint32_t>(nsample)) extra[pos] = v; }
+            // two lists per step, four entries per lane and list: eight independent loads in flight per lane
+            for (int p0 = warp; p0 < P; p0 += 2 * nwarps) {
+                const int pb[2] = {p0, p0 + nwarps};
+                const int nb[2] = {s_n[p0], p0 + nwarps < P ? s_n[p0 + nwarps] : 0};
+                const uint64_t* eb[2] = {lists + (static_cast<size_t>(pb[0]) * Qp + q) * cap,
+                                         lists + (static_cast<size_t>(pb[1] < P ? pb[1] : pb[0]) * Qp + q) * cap};
+                const int nmax = nb[0] > nb[1] ? nb[0] : nb[1];
+                for (int i0 = 0; i0 < nmax; i0 += 128) {
+                    uint64_t v[2][4];
+#pragma unroll
+                    for (int l = 0; l < 2; ++l)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * 32 + lane;
+                            v[l][u] = i < nb[l] ? ld_cg_u64(eb[l] + i) : 0ull;
+                        }
+#pragma unroll
+                    for (int l = 0; l < 2; ++l)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (v[l][u] >= tau0) {      // tau0 != 0: empty entries (0) never pass
+                                const uint32_t pos = atomicAdd(&nkeep, 1u);
+                                if (pos < static_cast<uint32_t>(nsample)) extra[pos] = v[l][u];
+                            }
                 }
             }
             __syncthreads();
@@ -616,12 +665,24 @@ merge_phase_warp_kernel(uint64_t* __restrict__ carry, uint64_t* __restrict__ tau
     uint64_t* cq = carry + static_cast<size_t>(q) * kpad;
     for (int j = lane; j < kpad; j += 32) { sC[w][j] = cq[j]; sN[w][j] = 0ull; }
     int off0 = incl - mine;
+    // a list holds one or two survivors as a rule: their loads are issued for all lists of the lane before the first
+    // use (a load-then-store loop per list would pay one L2 round trip per list, one after the other)
+    uint64_t first[kMwMaxPL][2];
+#pragma unroll
+    for (int i = 0; i < kMwMaxPL; ++i) {
+        const int p = lane + 32 * i;
+        const uint64_t* e = lists + (static_cast<size_t>(p < P ? p : 0) * Qp + q) * cap;
+        first[i][0] = cnt[i] > 0 ? ld_cg_u64(e) : 0ull;
+        first[i][1] = cnt[i] > 1 ? ld_cg_u64(e + 1) : 0ull;
+    }
 #pragma unroll
     for (int i = 0; i < kMwMaxPL; ++i) {
         const int p = lane + 32 * i;
         if (p < P) {
             const uint64_t* e = lists + (static_cast<size_t>(p) * Qp + q) * cap;
-            for (int j = 0; j < cnt[i]; ++j) sS[w][off0 + j] = ld_cg_u64(e + j);
+            if (cnt[i] > 0) sS[w][off0] = first[i][0];
+            if (cnt[i] > 1) sS[w][off0 + 1] = first[i][1];
+            for (int j = 2; j < cnt[i]; ++j) sS[w][off0 + j] = ld_cg_u64(e + j);
             off0 += cnt[i];
         }
     }
@@ -800,7 +861,9 @@ int launch_tc_batch(sky_bank* b, const float* t, int Q, int metric, int k, int64
         int pool = 4 * kpad > 2048 ? 4 * kpad : 2048, nsample = 2 * kpad > 1024 ? 2 * kpad : 1024;
         if (first) {
             const int64_t np_max = static_cast<int64_t>(grid) * kTileRows + k;
-            const int64_t want = round_up(2 * np_max * k / kMpSample, 1024);
+            // the k-th best of a sample of `pool` candidates keeps ~k np_max / pool of all of them: 1.5 x headroom under
+            // kMpSample (the count scatters by ~1 / sqrt(k)); a smaller pool lets two merge CTAs share an SM at k = 1000
+            const int64_t want = round_up(3 * np_max * k / (2 * kMpSample), 1024);
             pool = static_cast<int>(want < 4096 ? 4096 : (want > 16384 ? 16384 : want));
             nsample = kMpSample;
         }
