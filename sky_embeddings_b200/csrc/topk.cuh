@@ -343,15 +343,9 @@ __device__ uint64_t block_select_sort(Fetch fetch, int n, int k, int kpad, uint6
             const int shift = pass * 8;
             for (int b = tid; b < 256; b += nt) hist[b] = 0;
             __syncthreads();
-            // Lanes of a warp that hit the same bin add once (match.any): candidates of one query share the leading bytes
-            // of their keys, so in the first passes every thread would otherwise queue up on ONE shared-memory word.
-            for (int j0 = 0; j0 < n; j0 += nt) {
-                const int j = j0 + tid;
-                const uint64_t v = j < n ? fetch(j) : 0ull;
-                const bool in = v != 0 && (v & mask) == prefix;
-                const uint32_t digit = static_cast<uint32_t>(v >> shift) & 0xFFu;
-                const uint32_t peers = __match_any_sync(0xffffffffu, in ? digit : 0xFFFFFFFFu);
-                if (in && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], static_cast<uint32_t>(__popc(peers)));
+            for (int j = tid; j < n; j += nt) {
+                uint64_t v = fetch(j);
+                if (v != 0 && (v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 0xFF], 1u);
             }
             __syncthreads();
             if (tid < 32) {
