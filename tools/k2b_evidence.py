@@ -25,10 +25,12 @@ Timelines:    tools/trace_tb_phase.py <phase> (experiments build, SKY_TB_DEBUG=3
 """)
 for title, f, w in [("C3's shard at 8 GPUs (1.25 M x 768, Q = 4096, L2, k = 100): 4 epilogue warps + survivor queue", f'{G}/d_launches_1250000.csv', 2),
                     ("same, 8 epilogue warps", f'{G}/f8_launches_1.csv', 3),
-                    ("same, 8 epilogue warps + phase merges with independent loads / aggregated histogram atomics (final)", f'{G}/g_launches_1.csv', 3),
+                    ("same, 8 epilogue warps + phase merges with independent loads in flight (final)", f'{G}/h_launches_1.csv', 3),
+                    ("experiment, dropped: the above + warp-aggregated (match.any) histogram atomics in the radix select -- the merges get slower", f'{G}/g_launches_1.csv', 3),
                     ("C4's share at 8 GPUs (12.5 M x 768, Q = 1000, cosine, k = 1000): 4 epilogue warps + survivor queue", f'{G}/d_launches_12500000.csv', 2),
                     ("same, 8 epilogue warps", f'{G}/f8_launches_2.csv', 3),
-                    ("same, final", f'{G}/g_launches_2.csv', 3)]:
+                    ("same, final", f'{G}/h_launches_2.csv', 3),
+                    ("experiment, dropped: match.any histogram atomics", f'{G}/g_launches_2.csv', 3)]:
     if not os.path.exists(f): continue
     line, tot, sm = search_launches(f, w)
     print("== " + title)
