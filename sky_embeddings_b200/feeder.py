@@ -78,11 +78,12 @@ def bank_from_loader(model, dataloader, device, n_batches=None, max_pool=False, 
 
 
 def resident_simsearch(bank, target_latent, ra_decs, samples=None, num_extra_tokens=1, n_save=256, metric="cosine",
-                       combine="min", use_weights=True, max_pool=False, cls_token=False):
+                       combine="min", use_weights=True, max_pool=False, cls_token=False, model=None):
     """mae_simsearch over a resident bank: one search instead of a pass over the loader.
     Returns (best_samples or None, best_idx [n_save] i64, best_ra_decs [n_save, 2], best_scores [n_save]),
-    best first -- the reference's 4-tuple with the winners' bank indices in place of their re-encoded
-    latents (re-encode ``best_samples`` with the model if those are needed, utils/similarity.py:124-130)."""
+    best first -- the reference's 4-tuple with the winners' bank indices in place of their re-encoded latents.
+    With ``model`` (and ``samples``) the winners are re-encoded as the reference does (utils/similarity.py:124-130) and
+    the second element is ``best_latent`` [n_save, 1 + P, D]: exactly the reference's return value."""
     tsel = select_tokens(target_latent.to(bank.device), num_extra_tokens, cls_token, max_pool)
     t, w = bank.query_from_targets(tsel, use_weights)
     scores, idx = bank.search(t, w if use_weights else None, k=n_save, metric=metric, combine=combine)
@@ -94,6 +95,14 @@ def resident_simsearch(bank, target_latent, ra_decs, samples=None, num_extra_tok
     if samples is not None:
         best_samples = samples[safe.cpu()]
         best_samples[~ok.cpu()] = 0
+    if model is not None:
+        if best_samples is None:
+            raise ValueError("resident_simsearch(model=...) re-encodes the winners: pass the bank's `samples` as well")
+        enc = model.module if hasattr(model, "module") else model
+        best_samples = best_samples.to(bank.device)
+        with torch.no_grad():
+            best_latent, _, _ = enc.forward_features(best_samples, ra_dec=best_ra, reshape_out=False)
+        return best_samples, best_latent, best_ra, scores
     return best_samples, idx, best_ra, scores
 
 
