@@ -208,13 +208,36 @@ def make_queries(n_total, D, Q, dev, weighted, gen_seed=1234):
     return t.contiguous(), w, planted
 
 
-def build_bank(n_rows, D, dev, chunk0=0, dtype="bf16", L=1):
-    """Device-generated synthetic shard: chunks [chunk0, ...) of the global synthetic bank, normalised with the
-    statistics of the first 512 rows of global chunk 0 on every rank.  L > 1: every L consecutive rows form one
-    item of L patch tokens (n_rows counts rows)."""
+def shard_pieces(row0, n_rows, n_total):
+    """Rows [row0, row0 + n_rows) of the n_total-row synthetic bank as pieces of its generator chunks:
+    (chunk index, rows the chunk is generated with, first row inside the chunk, rows taken, destination row in the shard).
+    A chunk is always generated with its canonical size min(CHUNK_ROWS, n_total - chunk * CHUNK_ROWS) -- the values of a
+    torch Philox draw depend on its shape -- so a row is the same tensor whichever rank holds it and wherever the shard
+    boundaries fall (make_queries draws the planted rows the same way)."""
+    from sky_embeddings_b200 import synth
+    out, done = [], 0
+    while done < n_rows:
+        c, off = divmod(row0 + done, synth.CHUNK_ROWS)
+        chunk_rows = min(synth.CHUNK_ROWS, n_total - c * synth.CHUNK_ROWS)
+        take = min(chunk_rows - off, n_rows - done)
+        assert take > 0, "shard reaches past the end of the bank"
+        out.append((c, chunk_rows, off, take, done))
+        done += take
+    return out
+
+
+def build_bank(n_rows, D, dev, chunk0=0, dtype="bf16", L=1, row0=None, n_total=None):
+    """Device-generated synthetic shard, normalised with the statistics of the first 512 rows of global chunk 0 on every
+    rank.  Default: n_rows rows from generator chunk `chunk0` on (a stand-alone bank of n_rows rows).  With row0 / n_total:
+    rows [row0, row0 + n_rows) of the n_total-row global bank, any row0 (strong scaling: equal shards).  L > 1: every L
+    consecutive rows form one item of L patch tokens (n_rows counts rows)."""
     from sky_embeddings_b200 import Bank, synth
     bank = Bank(n_rows // L, L, D, dtype, dev)
     bank.fit_norm(raw_chunk(0, 512, D, dev).reshape(512 // L, L, D))
+    if row0 is not None:
+        for c, chunk_rows, off, take, dst in shard_pieces(row0, n_rows, n_total):
+            bank.upload(raw_chunk(c, chunk_rows, D, dev)[off:off + take].reshape(take // L, L, D), dst // L)
+        return bank.finalize()
     done, c = 0, chunk0
     while done < n_rows:
         rows = min(synth.CHUNK_ROWS, n_rows - done)
@@ -358,14 +381,19 @@ def run_search_workload(name, wl, args, dev, steps, warmup, strong, headline):
     dtype, L, weighted = wl.get("dtype", "bf16"), wl.get("L", 1), wl.get("weighted", False)
     esz = 2 if dtype == "bf16" else 4
     if strong:
-        row_lo, row_hi = shard_range(n, rank, world, align=synth.CHUNK_ROWS)
+        # equal shards: boundaries on bank tiles (128 rows), not on generator chunks -- with 65 536-row chunks rank 0 of 8
+        # held 1 310 720 of C3's 10 M rows against 1 245 184 on the others and set the pace of every step
+        row_lo, row_hi = shard_range(n, rank, world, align=128 * L)
         n_total = n
     else:
         chunks_per_rank = (n + synth.CHUNK_ROWS - 1) // synth.CHUNK_ROWS
         row_lo, row_hi = rank * chunks_per_rank * synth.CHUNK_ROWS, rank * chunks_per_rank * synth.CHUNK_ROWS + n
         n_total = n * world
     n_local = row_hi - row_lo
-    bank = build_bank(n_local, D, dev, chunk0=row_lo // synth.CHUNK_ROWS, dtype=dtype, L=L)
+    if strong:
+        bank = build_bank(n_local, D, dev, dtype=dtype, L=L, row0=row_lo, n_total=n)
+    else:
+        bank = build_bank(n_local, D, dev, chunk0=row_lo // synth.CHUNK_ROWS, dtype=dtype, L=L)
     # queries: planted neighbours of rows spread over the global bank (strong) / rank 0's shard (weak); identical on every rank
     t_dev, w_dev, planted = make_queries(n if (strong or world == 1) else n, D, Q, dev, weighted)
     t_host = t_dev.cpu().pin_memory()
