@@ -13,8 +13,10 @@
 // is appended to the CTA's candidate list.  Between phases a merge kernel folds the lists into the
 // running top-k ("carry") of every query and refreshes the bounds -- the running merge of
 // update_best_scores (utils/similarity.py:18-35), done once per phase instead of once per batch.
-// With doubling phases about k candidates per query survive per phase, so lists stay short; an
-// adversarially ordered bank is still exact: a list that fills up is pruned in place to its k best.
+// The bound is fixed inside a phase, so a phase lets k * (rows of the phase / rows before it) rows per query through
+// (at most ~3.2 k with phase sizes 1, 1, 4, 16, ... tiles per CTA), so lists stay short; an adversarially ordered bank
+// is still exact: a list that fills up is pruned in place to its k best.  Rows that pass the pre-filter are queued per
+// epilogue warp and scored exactly / inserted 32 at a time (see the epilogue).
 #include <cstdlib>
 
 #include "bank.cuh"
